@@ -1,0 +1,12 @@
+"""fastfp_b200 -- a B200-native engine for the pulsar-timing Fp-statistic frequency scan.
+
+Drop-in for the hot path of gabefreedman/fastfp (``FastFp.calculate_Fp``, ``NMFP.calculate_nmfp``,
+``fastfp.utils.get_xCy``): same Python call signatures, with the JAX/XLA kernels replaced by
+hand-written fp64 CUDA kernels for sm_100a behind a C ABI (``include/fastfp_b200.h``).
+"""
+from .fastfp import FastFp
+from .utils import get_mats_fp, get_mats_nmfp, get_xCy
+from .vmap import vmap
+
+__version__ = "0.1.0"
+__all__ = ["FastFp", "get_xCy", "get_mats_fp", "get_mats_nmfp", "vmap"]

@@ -1,0 +1,317 @@
+"""ctypes binding of ``libfastfp_b200.so`` (the C ABI of ``include/fastfp_b200.h``).
+
+The product path is the CUDA library; there is deliberately **no CPU fallback**: if the
+library is missing, or no CUDA device is visible, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Sequence
+
+import numpy as np
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libfastfp_b200.so")
+_lib = None
+
+c_double_p = C.POINTER(C.c_double)
+c_int64_p = C.POINTER(C.c_int64)
+c_double_pp = C.POINTER(c_double_p)
+
+FREQS_ON_DEVICE = 1
+OUT_ON_DEVICE = 2
+PARAMS_ON_DEVICE = 4
+
+# every symbol include/fastfp_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "fastfp_last_error": (C.c_char_p, []),
+    "fastfp_version": (C.c_int, []),
+    "fastfp_device_count": (C.c_int, []),
+    "fastfp_pack_create": (
+        C.c_int,
+        [C.c_int, C.c_int, c_int64_p, c_int64_p, c_double_pp, c_double_pp, c_double_pp, c_double_pp,
+         c_double_pp, C.c_void_p, C.POINTER(C.c_void_p)],
+    ),
+    "fastfp_fp_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "fastfp_fp_terms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "fastfp_nmfp_pack_create": (
+        C.c_int,
+        [C.c_int, C.c_int, c_int64_p, c_int64_p, c_double_pp, c_double_pp, c_double_pp, c_double_pp,
+         c_double_pp, c_int64_p, c_double_pp, C.c_void_p, C.POINTER(C.c_void_p)],
+    ),
+    "fastfp_nmfp_sweep": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p],
+    ),
+    "fastfp_powerlaw_phiinv": (
+        C.c_int,
+        [C.c_void_p, c_double_pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "fastfp_pack_destroy": (None, [C.c_void_p]),
+    "fastfp_pack_bytes": (C.c_int64, [C.c_void_p]),
+    "fastfp_pack_num_pulsars": (C.c_int, [C.c_void_p]),
+    "fastfp_pack_mvar_total": (C.c_int64, [C.c_void_p]),
+    "fastfp_kernel_launches": (C.c_int64, []),
+    "fastfp_xcy": (
+        C.c_int,
+        [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p],
+    ),
+    "fastfp_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
+    "fastfp_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+
+class FastFpError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise FastFpError(
+            f"{_LIB_PATH} is missing: build it with `python -m fastfp_b200.build` "
+            "(there is no CPU fallback for the Fp hot path)"
+        )
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().fastfp_last_error()
+        raise FastFpError(f"fastfp_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def require_device() -> int:
+    n = load().fastfp_device_count()
+    if n < 1:
+        raise FastFpError("no CUDA device visible: the Fp hot path only runs on a B200 (no CPU fallback)")
+    return n
+
+
+def as_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr_array(arrs: Sequence[np.ndarray]):
+    arr = (c_double_p * len(arrs))()
+    for i, a in enumerate(arrs):
+        arr[i] = a.ctypes.data_as(c_double_p)
+    return arr
+
+
+def _int64_array(vals: Sequence[int]):
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def _vp(x) -> C.c_void_p:
+    """host ndarray / integer device address -> void*"""
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    return C.c_void_p(int(x))
+
+
+def _check_lists(toas, residuals, Nvecs, Ts, mats, what):
+    P = len(toas)
+    if P < 1 or not (len(residuals) == len(Nvecs) == len(Ts) == len(mats) == P):
+        raise ValueError(f"toas, residuals, Nvecs, Ts and {what} must be lists of equal length P >= 1")
+    toas, residuals, Nvecs = [as_f64(a) for a in toas], [as_f64(a) for a in residuals], [as_f64(a) for a in Nvecs]
+    Ts, mats = [as_f64(a) for a in Ts], [as_f64(a) for a in mats]
+    n, m = [], []
+    for p in range(P):
+        if Ts[p].ndim != 2:
+            raise ValueError(f"Ts[{p}] must be 2-D (ntoa, nbasis)")
+        np_, mp_ = Ts[p].shape
+        if toas[p].shape != (np_,) or residuals[p].shape != (np_,) or Nvecs[p].shape != (np_,):
+            raise ValueError(
+                f"pulsar {p}: toas/residuals/Nvec must have shape ({np_},) to match Ts "
+                "(a diagonal N is required, as in the reference's get_xCy)"
+            )
+        if mats[p].shape != (mp_, mp_):
+            raise ValueError(f"pulsar {p}: {what} must have shape ({mp_}, {mp_})")
+        n.append(np_)
+        m.append(mp_)
+    return P, n, m, toas, residuals, Nvecs, Ts, mats
+
+
+class Pack:
+    """Owner of one ``fastfp_pack_t*``: the device-resident packed pulsar array."""
+
+    def __init__(self, handle, P: int, device: int, nmfp: bool, n, m):
+        self._h, self.P, self.device, self.nmfp = handle, P, device, nmfp
+        self.n, self.m = list(n), list(m)
+
+    @classmethod
+    def create_fp(cls, toas, residuals, Nvecs, Ts, sigmas, device: int = 0, stream: int = 0) -> "Pack":
+        lib = load()
+        require_device()
+        P, n, m, toas, residuals, Nvecs, Ts, sigmas = _check_lists(toas, residuals, Nvecs, Ts, sigmas, "sigmas")
+        h = C.c_void_p()
+        check(
+            lib.fastfp_pack_create(
+                device, P, _int64_array(n), _int64_array(m), _ptr_array(toas), _ptr_array(residuals),
+                _ptr_array(Nvecs), _ptr_array(Ts), _ptr_array(sigmas), C.c_void_p(stream), C.byref(h),
+            )
+        )
+        return cls(h, P, device, False, n, m)
+
+    @classmethod
+    def create_nmfp(cls, toas, residuals, Nvecs, Ts, TNTs, m_fix, phiinv_fix, device: int = 0, stream: int = 0):
+        lib = load()
+        require_device()
+        P, n, m, toas, residuals, Nvecs, Ts, TNTs = _check_lists(toas, residuals, Nvecs, Ts, TNTs, "TNTs")
+        if len(m_fix) != P or len(phiinv_fix) != P:
+            raise ValueError("m_fix and phiinv_fix must have one entry per pulsar")
+        pf = []
+        for p in range(P):
+            if not 0 <= int(m_fix[p]) <= m[p]:
+                raise ValueError(f"pulsar {p}: m_fix out of range")
+            a = as_f64(phiinv_fix[p]).reshape(-1)
+            if a.shape[0] != int(m_fix[p]):
+                raise ValueError(f"pulsar {p}: phiinv_fix must have m_fix entries")
+            pf.append(a if a.size else np.zeros(1))
+        h = C.c_void_p()
+        check(
+            lib.fastfp_nmfp_pack_create(
+                device, P, _int64_array(n), _int64_array(m), _ptr_array(toas), _ptr_array(residuals),
+                _ptr_array(Nvecs), _ptr_array(Ts), _ptr_array(TNTs), _int64_array(m_fix), _ptr_array(pf),
+                C.c_void_p(stream), C.byref(h),
+            )
+        )
+        return cls(h, P, device, True, n, m)
+
+    # -- sweeps -------------------------------------------------------------------------
+    def fp_sweep(self, freqs, out=None, stream: int = 0, terms: bool = False):
+        """``freqs``: host ndarray or ``(device_address, F)``; ``out``: None (a host array is
+        returned), a host ndarray, or an integer device address."""
+        lib = load()
+        flags = 0
+        if isinstance(freqs, tuple):
+            fptr, F = freqs
+            flags |= FREQS_ON_DEVICE
+        else:
+            freqs = as_f64(freqs).reshape(-1)
+            fptr, F = freqs, freqs.shape[0]
+        ret = None
+        if out is None:
+            ret = np.empty((self.P, F) if terms else (F,), dtype=np.float64)
+            optr = ret
+        elif isinstance(out, np.ndarray):
+            optr = out
+        else:
+            optr = out
+            flags |= OUT_ON_DEVICE
+        fn = lib.fastfp_fp_terms if terms else lib.fastfp_fp_sweep
+        check(fn(self._h, _vp(fptr), F, _vp(optr), flags, C.c_void_p(stream)))
+        return ret
+
+    def nmfp_sweep(self, freqs, phiinv_var, D: int, out=None, stream: int = 0):
+        lib = load()
+        flags = 0
+        if isinstance(freqs, tuple):
+            fptr, F = freqs
+            flags |= FREQS_ON_DEVICE
+        else:
+            freqs = as_f64(freqs).reshape(-1)
+            fptr, F = freqs, freqs.shape[0]
+        if isinstance(phiinv_var, np.ndarray):
+            phiinv_var = as_f64(phiinv_var)
+            pptr = phiinv_var
+        else:
+            pptr = phiinv_var
+            flags |= PARAMS_ON_DEVICE
+        ret = None
+        if out is None:
+            ret = np.empty((D, F), dtype=np.float64)
+            optr = ret
+        elif isinstance(out, np.ndarray):
+            optr = out
+        else:
+            optr = out
+            flags |= OUT_ON_DEVICE
+        check(lib.fastfp_nmfp_sweep(self._h, _vp(fptr), F, _vp(pptr), D, _vp(optr), flags, C.c_void_p(stream)))
+        return ret
+
+    def powerlaw_phiinv(self, Ffreqs, log10_A, gamma, curn_Ffreqs, curn_log10_A, curn_gamma, out_dev, stream=0):
+        """Device-side ``get_phiinv`` of the varying block for D draws (host params in)."""
+        lib = load()
+        Ff = [as_f64(a) for a in Ffreqs]
+        A, G = as_f64(log10_A), as_f64(gamma)
+        D = A.shape[0]
+        if curn_Ffreqs is not None and len(curn_Ffreqs):
+            cf, cA, cG = as_f64(curn_Ffreqs), as_f64(curn_log10_A), as_f64(curn_gamma)
+            args = (_vp(cf), cf.shape[0], _vp(cA), _vp(cG))
+        else:
+            args = (C.c_void_p(0), 0, C.c_void_p(0), C.c_void_p(0))
+        check(
+            lib.fastfp_powerlaw_phiinv(
+                self._h, _ptr_array(Ff), _vp(A), _vp(G), D, *args, C.c_void_p(int(out_dev)), C.c_void_p(stream)
+            )
+        )
+
+    @property
+    def mvar_total(self) -> int:
+        return int(load().fastfp_pack_mvar_total(self._h))
+
+    @property
+    def nbytes(self) -> int:
+        return int(load().fastfp_pack_bytes(self._h))
+
+    def close(self):
+        if self._h:
+            load().fastfp_pack_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def xcy(Nvec, T, sigma, x, y, device: int = 0, stream: int = 0) -> float:
+    lib = load()
+    require_device()
+    Nvec, T, sigma, x, y = as_f64(Nvec), as_f64(T), as_f64(sigma), as_f64(x), as_f64(y)
+    if T.ndim != 2:
+        raise ValueError("get_xCy: T must be 2-D (ntoa, nbasis)")
+    n, m = T.shape
+    if Nvec.shape != (n,) or x.shape != (n,) or y.shape != (n,) or sigma.shape != (m, m):
+        raise ValueError("get_xCy: shapes must be Nvec (n,), T (n,m), sigma (m,m), x (n,), y (n,)")
+    out = np.empty(1)
+    check(lib.fastfp_xcy(device, n, m, _vp(Nvec), _vp(T), _vp(sigma), _vp(x), _vp(y), _vp(out), C.c_void_p(stream)))
+    return float(out[0])
+
+
+def fp64_peak(kind: int = 0, iters: int = 20000, device: int = 0):
+    lib = load()
+    require_device()
+    tf, ms = C.c_double(), C.c_double()
+    check(lib.fastfp_fp64_peak(device, kind, iters, C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+def debug_trace(pack: "Pack", freqs) -> np.ndarray:
+    """Per-warp clock stamps of CTA 0, shape (64, 8, 4) (profiling aid)."""
+    freqs = as_f64(freqs)
+    tr = np.zeros((64, 8, 4), dtype=np.int64)
+    check(load().fastfp_debug_trace(pack._h, _vp(freqs), freqs.shape[0], _vp(tr)))
+    return tr
+
+
+def kernel_launches() -> int:
+    return int(load().fastfp_kernel_launches())

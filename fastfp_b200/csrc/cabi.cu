@@ -1,0 +1,425 @@
+// extern "C" entry points of libfastfp_b200.so (declared in include/fastfp_b200.h).
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+#include "../../include/fastfp_b200.h"
+#include "ffp_internal.cuh"
+
+namespace ffp {
+
+std::atomic<int64_t> g_launches{0};
+static thread_local std::string t_err;
+
+void set_error(const std::string& msg) { t_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  t_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return FASTFP_ERR_CUDA;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+static int ensure(T** buf, int64_t* cap, int64_t need) {
+  if (*cap >= need) return 0;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  FFP_CUDA(cudaMalloc(buf, (size_t)need * sizeof(T)));
+  *cap = need;
+  return 0;
+}
+
+// nmfp.cu
+int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res,
+                     const double* d_Nvec, const double* d_T, const double* d_TNT,
+                     const double* d_phiinv_fix, cudaStream_t st);
+int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F,
+                    const double* d_phiinv_var, int64_t D, double* d_out, cudaStream_t st);
+int powerlaw_phiinv_impl(const fastfp_pack* pk, const double* const* Ffreqs, const double* log10_A,
+                         const double* gamma, int64_t D, const double* curn_Ffreqs, int64_t ncurn,
+                         const double* curn_log10_A, const double* curn_gamma, double* out,
+                         cudaStream_t st);
+
+// Common part of the two pack constructors: validate, lay out, upload the raw arrays.
+struct Staging {
+  double *d_toas = nullptr, *d_res = nullptr, *d_Nvec = nullptr, *d_T = nullptr;
+  ~Staging() {
+    cudaFree(d_toas); cudaFree(d_res); cudaFree(d_Nvec); cudaFree(d_T);
+  }
+};
+
+static int pack_layout(fastfp_pack* pk, int P, const int64_t* n, const int64_t* m,
+                       const int64_t* m_fix) {
+  pk->P = P;
+  pk->meta.resize(P);
+  int64_t pk_off = 0, L_off = 0, raw_off = 0, T_off = 0;
+  int var_off = 0;
+  std::map<KernelCfg, std::vector<int>> groups;
+  for (int p = 0; p < P; ++p) {
+    if (n[p] < 1 || m[p] < 1 || n[p] > 0x7fffff00LL) {
+      set_error("pulsar " + std::to_string(p) + ": n and m must be positive");
+      return FASTFP_ERR_INVALID;
+    }
+    KernelCfg kc{};
+    if (!sweep_config((int)m[p], &kc)) {
+      set_error("pulsar " + std::to_string(p) + ": basis width m=" + std::to_string(m[p]) +
+                " exceeds the supported maximum " + std::to_string(MAX_M));
+      return FASTFP_ERR_UNSUPPORTED;
+    }
+    PulsarMeta& pm = pk->meta[p];
+    pm.n = (int)n[p];
+    pm.m = (int)m[p];
+    pm.ci = kc.ci;
+    pm.nch = (int)((n[p] + kc.ci - 1) / kc.ci);
+    pm.mpad = kc.mp();
+    pm.pk_off = pk_off;
+    pm.L_off = L_off;
+    pm.raw_off = raw_off;
+    pm.T_off = T_off;
+    pm.mfix = m_fix ? (int)m_fix[p] : pm.m;
+    pm.mvar = pm.m - pm.mfix;
+    if (pm.mfix < 0 || pm.mvar < 0) {
+      set_error("pulsar " + std::to_string(p) + ": m_fix out of range");
+      return FASTFP_ERR_INVALID;
+    }
+    pm.var_off = var_off;
+    var_off += pm.mvar;
+    pk->mvar_max = std::max(pk->mvar_max, pm.mvar);
+    pk_off += (int64_t)pm.nch * pm.ci * (3 + pm.mpad);
+    L_off += (int64_t)pm.m * pm.m;
+    raw_off += pm.n;
+    T_off += (int64_t)pm.n * pm.m;
+    groups[kc].push_back(p);
+  }
+  pk->mvar_total = var_off;
+  FFP_CUDA(cudaMalloc(&pk->d_meta, sizeof(PulsarMeta) * P));
+  FFP_CUDA(cudaMemcpy(pk->d_meta, pk->meta.data(), sizeof(PulsarMeta) * P, cudaMemcpyHostToDevice));
+  FFP_CUDA(cudaMalloc(&pk->d_packets, (size_t)pk_off * 8));
+  FFP_CUDA(cudaMalloc(&pk->d_L, (size_t)L_off * 8));
+  FFP_CUDA(cudaMalloc(&pk->d_info, sizeof(int) * P));
+  FFP_CUDA(cudaMemset(pk->d_info, 0, sizeof(int) * P));
+  FFP_CUDA(cudaDeviceGetAttribute(&pk->num_sms, cudaDevAttrMultiProcessorCount, pk->device));
+  const size_t slab_bytes = (size_t)2 * pk->num_sms * sweep_max_slab_doubles() * 8;
+  FFP_CUDA(cudaMalloc(&pk->d_slab, slab_bytes));
+  FFP_CUDA(cudaMalloc(&pk->d_counter, sizeof(unsigned int)));
+  pk->bytes = pk_off * 8 + L_off * 8 + (int64_t)sizeof(PulsarMeta) * P + (int64_t)slab_bytes;
+  for (auto& kv : groups) {
+    Group g;
+    g.cfg = kv.first;
+    g.count = (int)kv.second.size();
+    FFP_CUDA(cudaMalloc(&g.d_pidx, sizeof(int) * g.count));
+    FFP_CUDA(cudaMemcpy(g.d_pidx, kv.second.data(), sizeof(int) * g.count, cudaMemcpyHostToDevice));
+    pk->groups.push_back(g);
+  }
+  return 0;
+}
+
+static int upload_ragged(double** dst, const double* const* src, const fastfp_pack* pk, int which,
+                         cudaStream_t st) {
+  // which: 0 = length n_p, 1 = n_p*m_p (T), 2 = m_p*m_p
+  int64_t total = 0;
+  for (auto& pm : pk->meta)
+    total += which == 0 ? pm.n : which == 1 ? (int64_t)pm.n * pm.m : (int64_t)pm.m * pm.m;
+  if (*dst == nullptr) FFP_CUDA(cudaMalloc(dst, (size_t)total * 8));
+  int64_t off = 0;
+  for (int p = 0; p < pk->P; ++p) {
+    const PulsarMeta& pm = pk->meta[p];
+    const int64_t cnt = which == 0 ? pm.n : which == 1 ? (int64_t)pm.n * pm.m : (int64_t)pm.m * pm.m;
+    if (!src[p]) { set_error("null per-pulsar array"); return FASTFP_ERR_INVALID; }
+    FFP_CUDA(cudaMemcpyAsync(*dst + off, src[p], (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
+    off += cnt;
+  }
+  return 0;
+}
+
+static void pack_free(fastfp_pack* pk) {
+  if (!pk) return;
+  DeviceGuard g(pk->device);
+  for (auto& gr : pk->groups) cudaFree(gr.d_pidx);
+  cudaFree(pk->d_meta); cudaFree(pk->d_packets); cudaFree(pk->d_L); cudaFree(pk->d_info);
+  cudaFree(pk->d_S0); cudaFree(pk->d_zr); cudaFree(pk->d_slab); cudaFree(pk->d_counter);
+  cudaFree(pk->d_terms); cudaFree(pk->d_freqs); cudaFree(pk->d_out); cudaFree(pk->d_scratch);
+  delete pk;
+}
+
+}  // namespace ffp
+
+using namespace ffp;
+
+extern "C" {
+
+const char* fastfp_last_error(void) { return t_err.c_str(); }
+int fastfp_version(void) { return 100; }
+int fastfp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int64_t fastfp_kernel_launches(void) { return g_launches.load(); }
+
+int fastfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
+                       const double* const* toas, const double* const* residuals,
+                       const double* const* Nvecs, const double* const* Ts,
+                       const double* const* sigmas, void* stream, fastfp_pack_t** out) {
+  if (!out || P < 1 || !n || !m || !toas || !residuals || !Nvecs || !Ts || !sigmas) {
+    set_error("fastfp_pack_create: null argument or P < 1");
+    return FASTFP_ERR_INVALID;
+  }
+  *out = nullptr;
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select CUDA device " + std::to_string(device)); return FASTFP_ERR_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  fastfp_pack* pk = new fastfp_pack();
+  pk->device = device;
+  int rc = pack_layout(pk, P, n, m, nullptr);
+  Staging sg;
+  if (!rc) rc = upload_ragged(&sg.d_toas, toas, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_res, residuals, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_Nvec, Nvecs, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_T, Ts, pk, 1, st);
+  if (!rc) rc = upload_ragged(&pk->d_L, sigmas, pk, 2, st);
+  if (!rc) rc = launch_fp_precompute(pk, sg.d_toas, sg.d_res, sg.d_Nvec, sg.d_T, st);
+  if (rc) { pack_free(pk); return rc; }
+  *out = pk;
+  return FASTFP_OK;
+}
+
+int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
+                            const double* const* toas, const double* const* residuals,
+                            const double* const* Nvecs, const double* const* Ts,
+                            const double* const* TNTs, const int64_t* m_fix,
+                            const double* const* phiinv_fix, void* stream, fastfp_pack_t** out) {
+  if (!out || P < 1 || !n || !m || !toas || !residuals || !Nvecs || !Ts || !TNTs || !m_fix ||
+      !phiinv_fix) {
+    set_error("fastfp_nmfp_pack_create: null argument or P < 1");
+    return FASTFP_ERR_INVALID;
+  }
+  *out = nullptr;
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select CUDA device " + std::to_string(device)); return FASTFP_ERR_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  fastfp_pack* pk = new fastfp_pack();
+  pk->device = device;
+  pk->nmfp = true;
+  int rc = pack_layout(pk, P, n, m, m_fix);
+  Staging sg;
+  double *d_TNT = nullptr, *d_pf = nullptr;
+  if (!rc) rc = upload_ragged(&sg.d_toas, toas, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_res, residuals, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_Nvec, Nvecs, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_T, Ts, pk, 1, st);
+  if (!rc) rc = upload_ragged(&d_TNT, TNTs, pk, 2, st);
+  if (!rc) {
+    // fixed phiinv: (P, MAX_M) padded
+    std::vector<double> pf((size_t)P * MAX_M, 0.0);
+    for (int p = 0; p < P; ++p)
+      for (int j = 0; j < pk->meta[p].mfix; ++j) pf[(size_t)p * MAX_M + j] = phiinv_fix[p][j];
+    cudaError_t e = cudaMalloc(&d_pf, pf.size() * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_pf, pf.data(), pf.size() * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "upload phiinv_fix");
+  }
+  if (!rc) rc = nmfp_pack_finish(pk, sg.d_toas, sg.d_res, sg.d_Nvec, sg.d_T, d_TNT, d_pf, st);
+  cudaFree(d_TNT);
+  cudaFree(d_pf);
+  if (rc) { pack_free(pk); return rc; }
+  *out = pk;
+  return FASTFP_OK;
+}
+
+void fastfp_pack_destroy(fastfp_pack_t* pack) { pack_free(pack); }
+int64_t fastfp_pack_bytes(const fastfp_pack_t* pack) { return pack ? pack->bytes : 0; }
+int fastfp_pack_num_pulsars(const fastfp_pack_t* pack) { return pack ? pack->P : 0; }
+int64_t fastfp_pack_mvar_total(const fastfp_pack_t* pack) { return pack ? pack->mvar_total : 0; }
+
+// Frequencies are processed in batches so the (P, F_batch) term buffer stays bounded.
+static const int64_t kTermBudgetDoubles = 1LL << 27;  // 1 GiB
+
+static int fp_run(const fastfp_pack* pk, const double* freqs, int64_t F, double* out, int flags,
+                  void* stream, bool want_terms) {
+  if (!pk || (F > 0 && (!freqs || !out)) || F < 0) {
+    set_error("fastfp_fp_sweep: null argument or negative F");
+    return FASTFP_ERR_INVALID;
+  }
+  if (pk->nmfp) { set_error("this pack was built for nmfp; use fastfp_nmfp_sweep"); return FASTFP_ERR_INVALID; }
+  if (F == 0) return FASTFP_OK;
+  DeviceGuard g(pk->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fdev = flags & FASTFP_FREQS_ON_DEVICE, odev = flags & FASTFP_OUT_ON_DEVICE;
+  const double* d_freqs = freqs;
+  if (!fdev) {
+    if (int rc = ensure(&pk->d_freqs, &pk->freqs_cap, F)) return rc;
+    FFP_CUDA(cudaMemcpyAsync(pk->d_freqs, freqs, (size_t)F * 8, cudaMemcpyHostToDevice, st));
+    d_freqs = pk->d_freqs;
+  }
+  const int P = pk->P;
+  if (want_terms) {
+    double* d_terms = out;
+    if (!odev) {
+      if (int rc = ensure(&pk->d_terms, &pk->terms_cap, (int64_t)P * F)) return rc;
+      d_terms = pk->d_terms;
+    }
+    if (int rc = launch_fp_sweep(pk, d_freqs, F, d_terms, st)) return rc;
+    if (!odev) {
+      FFP_CUDA(cudaMemcpyAsync(out, d_terms, (size_t)P * F * 8, cudaMemcpyDeviceToHost, st));
+      FFP_CUDA(cudaStreamSynchronize(st));
+    }
+    return FASTFP_OK;
+  }
+  double* d_out = out;
+  if (!odev) {
+    if (int rc = ensure(&pk->d_out, &pk->out_cap, F)) return rc;
+    d_out = pk->d_out;
+  }
+  const int64_t FB = std::max<int64_t>(1024, std::min<int64_t>(F, kTermBudgetDoubles / P));
+  if (int rc = ensure(&pk->d_terms, &pk->terms_cap, (int64_t)P * std::min(FB, F))) return rc;
+  for (int64_t lo = 0; lo < F; lo += FB) {
+    const int64_t fb = std::min(FB, F - lo);
+    if (int rc = launch_fp_sweep(pk, d_freqs + lo, fb, pk->d_terms, st)) return rc;
+    if (int rc = launch_reduce_terms(pk->d_terms, P, fb, d_out + lo, st)) return rc;
+  }
+  if (!odev) {
+    FFP_CUDA(cudaMemcpyAsync(out, d_out, (size_t)F * 8, cudaMemcpyDeviceToHost, st));
+    FFP_CUDA(cudaStreamSynchronize(st));
+  }
+  return FASTFP_OK;
+}
+
+int fastfp_fp_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F, double* out,
+                    int flags, void* stream) {
+  return fp_run(pack, freqs, F, out, flags, stream, false);
+}
+int fastfp_fp_terms(const fastfp_pack_t* pack, const double* freqs, int64_t F, double* terms,
+                    int flags, void* stream) {
+  return fp_run(pack, freqs, F, terms, flags, stream, true);
+}
+
+int fastfp_nmfp_sweep(const fastfp_pack_t* pk, const double* freqs, int64_t F,
+                      const double* phiinv_var, int64_t D, double* out, int flags, void* stream) {
+  if (!pk || F < 0 || D < 0 || ((F > 0 && D > 0) && (!freqs || !phiinv_var || !out))) {
+    set_error("fastfp_nmfp_sweep: null argument or negative size");
+    return FASTFP_ERR_INVALID;
+  }
+  if (!pk->nmfp) { set_error("this pack was built for plain Fp; use fastfp_fp_sweep"); return FASTFP_ERR_INVALID; }
+  if (F == 0 || D == 0) return FASTFP_OK;
+  DeviceGuard g(pk->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fdev = flags & FASTFP_FREQS_ON_DEVICE, odev = flags & FASTFP_OUT_ON_DEVICE,
+             pdev = flags & FASTFP_PARAMS_ON_DEVICE;
+  const double* d_freqs = freqs;
+  if (!fdev) {
+    if (int rc = ensure(&pk->d_freqs, &pk->freqs_cap, F)) return rc;
+    FFP_CUDA(cudaMemcpyAsync(pk->d_freqs, freqs, (size_t)F * 8, cudaMemcpyHostToDevice, st));
+    d_freqs = pk->d_freqs;
+  }
+  const double* d_phi = phiinv_var;
+  double* d_phi_tmp = nullptr;
+  if (!pdev) {
+    FFP_CUDA(cudaMalloc(&d_phi_tmp, (size_t)D * pk->mvar_total * 8));
+    FFP_CUDA(cudaMemcpyAsync(d_phi_tmp, phiinv_var, (size_t)D * pk->mvar_total * 8,
+                             cudaMemcpyHostToDevice, st));
+    d_phi = d_phi_tmp;
+  }
+  double* d_out = out;
+  if (!odev) {
+    if (int rc = ensure(&pk->d_out, &pk->out_cap, D * F)) { cudaFree(d_phi_tmp); return rc; }
+    d_out = pk->d_out;
+  }
+  int rc = nmfp_sweep_impl(pk, d_freqs, F, d_phi, D, d_out, st);
+  if (!rc && !odev) {
+    cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t)D * F * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "copy nmfp result to host");
+  }
+  if (d_phi_tmp) { cudaStreamSynchronize(st); cudaFree(d_phi_tmp); }
+  return rc;
+}
+
+int fastfp_powerlaw_phiinv(const fastfp_pack_t* pk, const double* const* Ffreqs,
+                           const double* log10_A, const double* gamma, int64_t D,
+                           const double* curn_Ffreqs, int64_t ncurn, const double* curn_log10_A,
+                           const double* curn_gamma, double* phiinv_var_dev, void* stream) {
+  if (!pk || !pk->nmfp || !Ffreqs || !log10_A || !gamma || D < 0 || !phiinv_var_dev ||
+      (ncurn > 0 && (!curn_Ffreqs || !curn_log10_A || !curn_gamma))) {
+    set_error("fastfp_powerlaw_phiinv: invalid argument");
+    return FASTFP_ERR_INVALID;
+  }
+  if (D == 0) return FASTFP_OK;
+  DeviceGuard g(pk->device);
+  return powerlaw_phiinv_impl(pk, Ffreqs, log10_A, gamma, D, curn_Ffreqs, ncurn, curn_log10_A,
+                              curn_gamma, phiinv_var_dev, (cudaStream_t)stream);
+}
+
+int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
+               const double* sigma, const double* x, const double* y, double* out, void* stream) {
+  if (n < 1 || m < 1 || !Nvec || !T || !sigma || !x || !y || !out) {
+    set_error("fastfp_xcy: null argument or non-positive size");
+    return FASTFP_ERR_INVALID;
+  }
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select CUDA device " + std::to_string(device)); return FASTFP_ERR_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t tot = (size_t)(3 * n + n * m + m * m) + (size_t)(m * m + 3 * m + 2);
+  double* d = nullptr;
+  FFP_CUDA(cudaMalloc(&d, tot * 8));
+  double *dN = d, *dx = dN + n, *dy = dx + n, *dT = dy + n, *dS = dT + n * m, *dW = dS + m * m;
+  double* dO = dW + (m * m + 3 * m);
+  cudaError_t e = cudaMemcpyAsync(dN, Nvec, n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dT, T, n * m * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dS, sigma, m * m * 8, cudaMemcpyHostToDevice, st);
+  int rc = 0;
+  if (e != cudaSuccess) rc = cuda_fail(e, "fastfp_xcy upload");
+  if (!rc) rc = launch_xcy(n, m, dN, dT, dS, dx, dy, dW, dO, st);
+  if (!rc) {
+    e = cudaMemcpyAsync(out, dO, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "fastfp_xcy download");
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// profiling aid: run one sweep with per-warp clock stamps of CTA 0 ([64 chunks][8 warps][4]).
+int fastfp_debug_trace(const fastfp_pack_t* pk, const double* freqs, int64_t F, long long* trace_host) {
+  if (!pk || !freqs || F < 1 || !trace_host) { set_error("fastfp_debug_trace: invalid argument"); return FASTFP_ERR_INVALID; }
+  DeviceGuard g(pk->device);
+  double *df = nullptr, *dt = nullptr;
+  long long* dtr = nullptr;
+  const size_t nt = 64 * 8 * 4;
+  FFP_CUDA(cudaMalloc(&df, F * 8));
+  FFP_CUDA(cudaMalloc(&dt, (size_t)pk->P * F * 8));
+  FFP_CUDA(cudaMalloc(&dtr, nt * 8));
+  FFP_CUDA(cudaMemset(dtr, 0, nt * 8));
+  FFP_CUDA(cudaMemcpy(df, freqs, F * 8, cudaMemcpyHostToDevice));
+  int rc = launch_fp_sweep(pk, df, F, dt, 0, nullptr, dtr);
+  if (!rc) {
+    cudaError_t e = cudaMemcpy(trace_host, dtr, nt * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = cuda_fail(e, "trace copy");
+  }
+  cudaFree(df); cudaFree(dt); cudaFree(dtr);
+  return rc;
+}
+
+int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms) {
+  if (!tflops || !ms || iters < 1 || kind < 0 || kind > 4) {
+    set_error("fastfp_fp64_peak: invalid argument");
+    return FASTFP_ERR_INVALID;
+  }
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return FASTFP_ERR_CUDA; }
+  return run_fp64_peak(kind, iters, tflops, ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// Internal declarations shared by the CUDA translation units of libfastfp_b200.so.
+// sm_100a only (built with -gencode arch=compute_100a,code=sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+namespace ffp {
+
+// ---- tiling constants of the sweep kernel -------------------------
+constexpr int NW = 4;          // warps per sweep CTA (two CTAs are resident per SM)
+constexpr int NT = NW * 32;    // threads per sweep CTA
+constexpr int GST = 2;         // G-tile ring depth (TMA bulk copies)
+constexpr int VST = 4;         // TOA-vector ring depth (t | 1/N | w)
+constexpr int FLUSH_TOAS = 512;  // level-1 accumulation block, in TOAs
+constexpr int MAX_M = 256;     // widest basis the sweep kernel handles
+
+// Sweep configuration.
+//   TM  rows of G per thread           TQ  frequencies per thread (2*TQ columns: sin, cos)
+//   WMW warps along the basis (row) direction, NW/WMW along frequency
+//   CI  TOAs per staged chunk
+template <int TM_, int TQ_, int WMW_, int CI_>
+struct SweepCfg {
+  static constexpr int TM = TM_, TQ = TQ_, WMW = WMW_, CI = CI_;
+  static constexpr int WNW = NW / WMW;         // warps along frequency
+  static constexpr int KF = WNW * 8 * TQ;      // frequencies per CTA
+  static constexpr int MP = WMW * 4 * TM;      // padded basis width (rows of G)
+  static constexpr int SROW = 2 * KF;          // doubles per TOA row of the sin/cos tile
+  static constexpr int VEC = 3 * CI;           // doubles of the vector part: t | 1/N | w
+  static constexpr int GT = CI * MP;           // doubles of the G part: G[CI][MP]
+  static constexpr int PK = VEC + GT;          // doubles per packet
+  static constexpr int IG = NT / KF;           // TOA groups in the basis-building phase
+  static constexpr int IPT = CI / IG;          // TOAs per thread per chunk in that phase
+  static constexpr int NACC = TM * 2 * TQ;     // accumulators per thread
+  static constexpr int SLAB = (NACC + 5) * NT; // doubles of level-2 scratch per CTA
+  static constexpr int FLUSH = FLUSH_TOAS / CI;  // chunks per level-1 block
+  static constexpr size_t SMEM = (size_t)(2 * CI * SROW + GST * GT + VST * VEC) * 8 + 128;
+  static_assert(NT % KF == 0 && CI % IG == 0, "basis-phase mapping");
+};
+
+// Per-pulsar descriptor, device-visible.
+struct PulsarMeta {
+  int64_t pk_off;  // offset (in doubles) of the pulsar's first packet inside `packets`
+  int64_t L_off;   // offset of its m x m factor inside `Lbuf`
+  int64_t raw_off; // offset of its TOA-length vectors inside the staging arrays
+  int64_t T_off;   // offset of its raw T inside the staging array
+  int32_t n, m, nch, mpad;
+  int32_t mfix, mvar;  // nmfp: leading draw-independent columns / trailing per-draw columns
+  int32_t var_off;     // nmfp: offset of this pulsar's varying block in a phiinv_var row
+  int32_t ci;          // TOAs per packet for this pulsar's kernel configuration
+};
+
+struct KernelCfg {  // run-time mirror of SweepCfg's parameters
+  int tm, tq, wmw, ci;
+  int kf() const { return (NW / wmw) * 8 * tq; }
+  int mp() const { return wmw * 4 * tm; }
+  int slab() const { return (tm * 2 * tq + 5) * NT; }
+  bool operator<(const KernelCfg& o) const {
+    if (tm != o.tm) return tm < o.tm;
+    if (tq != o.tq) return tq < o.tq;
+    if (wmw != o.wmw) return wmw < o.wmw;
+    return ci < o.ci;
+  }
+};
+
+struct Group {  // pulsars that share one kernel instantiation
+  KernelCfg cfg;
+  int count;
+  int* d_pidx;  // device array of pulsar indices
+};
+
+}  // namespace ffp
+
+// The opaque handle of include/fastfp_b200.h.
+struct fastfp_pack {
+  int device = 0;
+  int P = 0;
+  int num_sms = 0;
+  bool nmfp = false;
+  std::vector<ffp::PulsarMeta> meta;
+  std::vector<ffp::Group> groups;
+  ffp::PulsarMeta* d_meta = nullptr;
+  double* d_packets = nullptr;  // [sum_p nch_p][PK_p]
+  double* d_L = nullptr;        // Cholesky factors (Fp) / fixed-block factors (nmfp)
+  int* d_info = nullptr;        // per-pulsar factorisation status
+  double* d_slab = nullptr;     // level-2 accumulation scratch, one slab per resident CTA
+  unsigned int* d_counter = nullptr;  // persistent-CTA work counter
+  int64_t bytes = 0;
+  int64_t mvar_total = 0;
+  int mvar_max = 0;
+  // nmfp only
+  double* d_S0 = nullptr;  // [P][mvmax][mvmax] Schur complement of the fixed block (no phiinv)
+  double* d_zr = nullptr;  // [P][mvmax]  z'_r
+  // scratch reused across sweeps (grown on demand)
+  mutable double* d_terms = nullptr;
+  mutable int64_t terms_cap = 0;
+  mutable double* d_freqs = nullptr;
+  mutable int64_t freqs_cap = 0;
+  mutable double* d_out = nullptr;
+  mutable int64_t out_cap = 0;
+  mutable double* d_scratch = nullptr;
+  mutable int64_t scratch_cap = 0;
+};
+
+namespace ffp {
+
+extern std::atomic<int64_t> g_launches;
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define FFP_CUDA(call)                                         \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) return ffp::cuda_fail(e__, #call); \
+  } while (0)
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------
+// precompute.cu
+int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_res,
+                         const double* d_Nvec, const double* d_T, cudaStream_t st);
+// fp_sweep*.cu
+struct NmfpOut {      // stage-A outputs of the nmfp path (null for plain Fp)
+  double* Z;          // [P][F][2][mvmax]  z'_s, z'_c
+  double* A;          // [P][F][5]         a_ss, a_sc, a_cc, a_sr, a_cr
+  int mvmax;
+};
+int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
+                    cudaStream_t st, const NmfpOut* nm = nullptr, long long* trace = nullptr);
+int launch_reduce_terms(const double* d_terms, int P, int64_t F, double* d_out, cudaStream_t st);
+bool sweep_config(int m, KernelCfg* cfg);
+int sweep_max_slab_doubles();
+// xcy.cu
+int launch_xcy(int64_t n, int64_t m, const double* dN, const double* dT, const double* dS,
+               const double* dx, const double* dy, double* d_work, double* d_out, cudaStream_t st);
+// microbench.cu
+int run_fp64_peak(int kind, int iters, double* tflops, double* ms);
+
+// ---- small PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      " selp.b32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+}  // namespace ffp

@@ -1,0 +1,77 @@
+// Branch-free double-precision sincos for the Earth-term basis.
+//
+// The sweep kernel needs sin and cos of phi = ((2*pi)*f)*t (reference fastfp/fastfp.py:78-79)
+// for ~1e11 (frequency, TOA) pairs per sweep; |phi| is a few 1e4 rad at most (t ~ 4.6e9 s,
+// f <= 1e-6 Hz). CUDA's sincos() keeps a Payne-Hanek slow path behind a call, which turns every
+// evaluation into its own control-flow region and stops the compiler from interleaving the
+// independent evaluations a thread owns. This version is straight-line code:
+//   k = rint(phi * 2/pi); r = phi - k*pi/2 by a three-constant Cody-Waite reduction with FMAs
+//   (exact products, so the only error is the final rounding of r: <= 2^-53*|r| + 2e-33*|k|);
+//   sin/cos kernels on |r| <= pi/4 with the fdlibm minimax coefficients; quadrant fix-up by
+//   selects. Valid for |phi| <= FFP_SINCOS_MAX (k fits comfortably in 2^17); callers route larger
+//   arguments to the library function. Measured max error vs long double: < 1 ulp-ish
+//   (tests/test_sincos_host.py pins it).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define FFP_HD __host__ __device__ __forceinline__
+#else
+#define FFP_HD inline
+#endif
+
+#define FFP_SINCOS_MAX 1.0e5
+
+namespace ffp {
+
+FFP_HD double ffp_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return std::fma(a, b, c);
+#endif
+}
+
+FFP_HD void sincos_cw(double x, double* sp, double* cp) {
+  // k = nearest integer to x*(2/pi), via the 1.5*2^52 magic constant (round-to-nearest-even)
+  const double magic = 6755399441055744.0;
+  const double kd = ffp_fma(x, 0.6366197723675814, magic);
+#if defined(__CUDA_ARCH__)
+  const int q = __double2loint(kd);
+#else
+  int64_t bits;
+  std::memcpy(&bits, &kd, 8);
+  const int q = (int)(uint32_t)bits;
+#endif
+  const double k = kd - magic;
+  double r = ffp_fma(-k, 1.5707963267948966, x);
+  r = ffp_fma(-k, 6.123233995736766e-17, r);
+  r = ffp_fma(-k, -1.4973849048591698e-33, r);
+  const double z = r * r;
+  // sin(r) = r + r*z*(S1 + z*(S2 + ... z*S6))
+  double ps = ffp_fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = ffp_fma(z, ps, 2.75573137070700676789e-06);
+  ps = ffp_fma(z, ps, -1.98412698298579493134e-04);
+  ps = ffp_fma(z, ps, 8.33333333332248946124e-03);
+  ps = ffp_fma(z, ps, -1.66666666666666324348e-01);
+  const double s = ffp_fma(r * z, ps, r);
+  // cos(r) = 1 - z/2 + z*z*(C1 + z*(C2 + ... z*C6))
+  double pc = ffp_fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = ffp_fma(z, pc, -2.75573143513906633035e-07);
+  pc = ffp_fma(z, pc, 2.48015872894767294178e-05);
+  pc = ffp_fma(z, pc, -1.38888888888741095749e-03);
+  pc = ffp_fma(z, pc, 4.16666666666666019037e-02);
+  const double c = ffp_fma(z, ffp_fma(z, pc, -0.5), 1.0);
+  // quadrant: k mod 4 = 0:(s,c) 1:(c,-s) 2:(-s,-c) 3:(-c,s)
+  const bool swap = (q & 1) != 0;
+  double so = swap ? c : s;
+  double co = swap ? s : c;
+  if (q & 2) so = -so;
+  if ((q + 1) & 2) co = -co;
+  *sp = so;
+  *cp = co;
+}
+
+}  // namespace ffp

@@ -1,0 +1,144 @@
+// One-time, frequency-independent per-pulsar work for the plain-Fp path:
+//   Sigma = L L^T,  G = L^-1 T^T N^-1  (m x n),  u_r = G r,  w = C^-1 r = N^-1 r - G^T u_r
+// and the packed, tile-contiguous layout the sweep kernel streams with one TMA bulk copy per
+// chunk: packet = [ t[CI] | 1/N[CI] | w[CI] | G[CI][MP] ]  (CI = 16 or 32 TOAs, per pulsar).
+//
+// The reference recomputes all of this for every frequency: T^T N^-1 x twice per get_xCy
+// (fastfp/utils.py:51-52) and an LU solve of Sigma per call (utils.py:54), six calls per
+// (frequency, pulsar) (fastfp/fastfp.py:81-88). With Sigma = L L^T,
+//   (x|y) = x^T N^-1 y - (G x).(G y)        and       (x|r) = x . w
+// so the per-frequency work collapses to Y = G [s c] plus five weighted dot products.
+#include "ffp_internal.cuh"
+
+namespace ffp {
+
+// In-place lower Cholesky of the m x m matrix at Lbuf + L_off (row-major; the strictly upper
+// part is left untouched and never read). One CTA per pulsar. info[p] = j+1 if pivot j is
+// not positive (the factor then carries NaN, which propagates like the reference's
+// non-raising jnp.linalg.solve on a singular Sigma).
+__global__ void chol_kernel(double* __restrict__ Lbuf, const PulsarMeta* __restrict__ meta,
+                            int* __restrict__ info) {
+  const PulsarMeta pm = meta[blockIdx.x];
+  const int m = pm.m;
+  double* A = Lbuf + pm.L_off;
+  __shared__ double djj;
+  for (int j = 0; j < m; ++j) {
+    if (threadIdx.x == 0) {
+      const double d = A[(size_t)j * m + j];
+      if (!(d > 0.0) && info[blockIdx.x] == 0) info[blockIdx.x] = j + 1;
+      djj = sqrt(d);
+      A[(size_t)j * m + j] = djj;
+    }
+    __syncthreads();
+    const double d = djj;
+    for (int i = j + 1 + threadIdx.x; i < m; i += blockDim.x)
+      A[(size_t)i * m + j] = A[(size_t)i * m + j] / d;
+    __syncthreads();
+    const int cnt = m - j - 1;
+    for (int idx = threadIdx.x; idx < cnt * cnt; idx += blockDim.x) {
+      const int ii = idx / cnt, kk = idx - ii * cnt;
+      if (kk <= ii) {
+        const int i = j + 1 + ii, k = j + 1 + kk;
+        A[(size_t)i * m + k] =
+            fma(-A[(size_t)i * m + j], A[(size_t)k * m + j], A[(size_t)i * m + k]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// One thread per (padded) TOA: forward-substitute L g = T_i^T / N_i and scatter t, 1/N and g
+// into the packet layout. Padded TOAs get zeros (weight 0: they add nothing to any sum).
+__global__ void build_packets_kernel(double* __restrict__ packets,
+                                     const PulsarMeta* __restrict__ meta,
+                                     const double* __restrict__ Lbuf,
+                                     const double* __restrict__ toas,
+                                     const double* __restrict__ Nvec,
+                                     const double* __restrict__ T) {
+  const PulsarMeta pm = meta[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int CI = pm.ci;
+  if (i >= pm.nch * CI) return;
+  const int m = pm.m, mp = pm.mpad;
+  const int pkw = CI * (3 + mp);
+  double* pk = packets + pm.pk_off + (size_t)(i / CI) * pkw;
+  const int il = i % CI;
+  const bool valid = i < pm.n;
+  const double ninv = valid ? 1.0 / Nvec[pm.raw_off + i] : 0.0;
+  pk[il] = valid ? toas[pm.raw_off + i] : 0.0;
+  pk[CI + il] = ninv;
+  pk[2 * CI + il] = 0.0;  // w, filled by w_kernel
+  double* grow = pk + 3 * CI + (size_t)il * mp;
+  if (!valid) {
+    for (int j = 0; j < mp; ++j) grow[j] = 0.0;
+    return;
+  }
+  const double* L = Lbuf + pm.L_off;
+  const double* Ti = T + pm.T_off + (size_t)i * m;
+  // g lives in the packet row itself (read-back hits L1/L2); m is small.
+  for (int j = 0; j < m; ++j) {
+    double acc = Ti[j] * ninv;
+    const double* Lj = L + (size_t)j * m;
+    for (int k = 0; k < j; ++k) acc = fma(-Lj[k], grow[k], acc);
+    grow[j] = acc / Lj[j];
+  }
+  for (int j = m; j < mp; ++j) grow[j] = 0.0;
+}
+
+// u_r[j] = sum_i G[j][i] r_i. One CTA per pulsar, one warp per basis row at a time; lanes
+// stride over TOAs, fixed-order shuffle tree: deterministic.
+__global__ void ur_kernel(const double* __restrict__ packets, const PulsarMeta* __restrict__ meta,
+                          const double* __restrict__ res, double* __restrict__ ur) {
+  const PulsarMeta pm = meta[blockIdx.x];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int CI = pm.ci;
+  const int mp = pm.mpad, pkw = CI * (3 + mp);
+  const double* pk0 = packets + pm.pk_off;
+  for (int j = wid; j < pm.m; j += nw) {
+    double acc = 0.0;
+    for (int i = lane; i < pm.n; i += 32) {
+      const double g = pk0[(size_t)(i / CI) * pkw + 3 * CI + (size_t)(i % CI) * mp + j];
+      acc = fma(g, res[pm.raw_off + i], acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) ur[(size_t)blockIdx.x * MAX_M + j] = acc;
+  }
+}
+
+// w_i = r_i / N_i - sum_j G[j][i] u_r[j]   (= (C^-1 r)_i)
+__global__ void w_kernel(double* __restrict__ packets, const PulsarMeta* __restrict__ meta,
+                         const double* __restrict__ res, const double* __restrict__ ur) {
+  const PulsarMeta pm = meta[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pm.n) return;
+  const int CI = pm.ci;
+  const int mp = pm.mpad, pkw = CI * (3 + mp);
+  double* pk = packets + pm.pk_off + (size_t)(i / CI) * pkw;
+  const int il = i % CI;
+  const double* grow = pk + 3 * CI + (size_t)il * mp;
+  const double* u = ur + (size_t)blockIdx.y * MAX_M;
+  double acc = 0.0;
+  for (int j = 0; j < pm.m; ++j) acc = fma(grow[j], u[j], acc);
+  pk[2 * CI + il] = res[pm.raw_off + i] * pk[CI + il] - acc;
+}
+
+int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_res,
+                         const double* d_Nvec, const double* d_T, cudaStream_t st) {
+  const int P = pk->P;
+  int nmax = 0;
+  for (auto& m : pk->meta) nmax = m.nch * m.ci > nmax ? m.nch * m.ci : nmax;
+  double* d_ur = nullptr;
+  FFP_CUDA(cudaMalloc(&d_ur, (size_t)P * MAX_M * sizeof(double)));
+  chol_kernel<<<P, 256, 0, st>>>(pk->d_L, pk->d_meta, pk->d_info);
+  dim3 g1((nmax + 127) / 128, P);
+  build_packets_kernel<<<g1, 128, 0, st>>>(pk->d_packets, pk->d_meta, pk->d_L, d_toas, d_Nvec, d_T);
+  ur_kernel<<<P, 256, 0, st>>>(pk->d_packets, pk->d_meta, d_res, d_ur);
+  w_kernel<<<g1, 128, 0, st>>>(pk->d_packets, pk->d_meta, d_res, d_ur);
+  g_launches += 4;
+  FFP_CUDA(cudaGetLastError());
+  FFP_CUDA(cudaStreamSynchronize(st));
+  FFP_CUDA(cudaFree(d_ur));
+  return 0;
+}
+
+}  // namespace ffp

@@ -59,6 +59,28 @@ class SynthPTA:
     def P(self) -> int:
         return len(self.psrs)
 
+    # the four accessors of an ``enterprise`` PTA that ``get_mats_fp`` / ``get_mats_nmfp`` call
+    # (reference ``fastfp/utils.py:72-75, 97-99``)
+    def get_phiinv(self, noise=None):
+        return [1.0 / phi for phi in self.phis]
+
+    def get_TNT(self, noise=None):
+        return self.TNTs
+
+    def get_ndiag(self, noise=None):
+        return self.Nvecs
+
+    def get_basis(self, noise=None):
+        return self.Ts
+
+    @property
+    def toas(self):
+        return [q.toas for q in self.psrs]
+
+    @property
+    def residuals(self):
+        return [q.residuals for q in self.psrs]
+
 
 def _timing_basis(t: np.ndarray, n_tm: int) -> np.ndarray:
     """Left singular vectors of a toy timing-model design matrix (mirrors

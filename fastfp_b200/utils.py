@@ -1,0 +1,53 @@
+"""Drop-in for the hot-path part of the reference's ``fastfp/utils.py``.
+
+* :func:`get_xCy` -- ``fastfp/utils.py:26-54``, run on the device through the C ABI.
+* :func:`get_mats_fp` / :func:`get_mats_nmfp` -- ``fastfp/utils.py:57-101``: they only *collect*
+  matrices from an ``enterprise`` PTA-like object (anything with ``get_phiinv``, ``get_TNT``,
+  ``get_ndiag``, ``get_basis``); the return orders differ exactly as in the reference.
+* :func:`initialize_pta` -- ``fastfp/utils.py:104-163`` needs the third-party ``enterprise``
+  packages and is out of this engine's scope; it raises a clear
+  error when they are absent.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+
+
+def get_xCy(Nvec, T, sigma, x, y, device: int = 0):
+    """``x^T C^-1 y`` with ``C = N + T B T^T`` and diagonal ``N`` (reference ``utils.py:49-54``).
+
+    Like the reference this does not apply to a block-diagonal ``N`` (``utils.py:29-31``);
+    a non-vector ``Nvec`` raises ``ValueError``."""
+    return np.float64(_cabi.xcy(Nvec, T, sigma, x, y, device=device))
+
+
+def get_mats_fp(pta, noise):
+    """``(Nvecs, Ts, sigmas)`` for the plain Fp-statistic (reference ``utils.py:57-78``)."""
+    phiinvs = pta.get_phiinv(noise)
+    TNTs = pta.get_TNT(noise)
+    Nvecs = pta.get_ndiag(noise)
+    Ts = pta.get_basis(noise)
+    sigmas = [np.asarray(TNT, dtype=np.float64) + np.diag(np.asarray(phiinv, dtype=np.float64))
+              for TNT, phiinv in zip(TNTs, phiinvs)]
+    return Nvecs, Ts, sigmas
+
+
+def get_mats_nmfp(pta, noise):
+    """``(TNTs, Nvecs, Ts)`` for the noise-marginalised statistic (reference ``utils.py:81-101``;
+    note the order differs from :func:`get_mats_fp`)."""
+    TNTs = pta.get_TNT(noise)
+    Nvecs = pta.get_ndiag(noise)
+    Ts = pta.get_basis(noise)
+    return TNTs, Nvecs, Ts
+
+
+def initialize_pta(*args, **kwargs):
+    """Model construction with ``enterprise`` (reference ``utils.py:104-163``): out of scope for
+    this engine; build the PTA with the reference's own helper and pass it to
+    :func:`get_mats_fp` / :func:`get_mats_nmfp`."""
+    raise NotImplementedError(
+        "initialize_pta builds an enterprise PTA (third-party model construction) and is not part "
+        "of the B200 hot path; construct the PTA with enterprise/fastfp and hand it to get_mats_*"
+    )

@@ -1,0 +1,137 @@
+/* fastfp_b200 -- C ABI of the B200-native Fp-statistic engine (libfastfp_b200.so).
+ *
+ * The reference (gabefreedman/fastfp @ 74b0ef8) is pure Python/JAX: it has no FFI of its
+ * own. Its hot-path boundary is the Python API
+ *     fastfp.utils.get_xCy(Nvec, T, sigma, x, y)                      fastfp/utils.py:27
+ *     FastFp.calculate_Fp(fgw, Nvecs, Ts, sigmas)  (+ jax.vmap over fgw) fastfp/fastfp.py:52,
+ *                                                                     examples/run_fp.py:63
+ *     NMFP.calculate_nmfp(fgw, samples, Nvecs, Ts, TNTs) (+ double vmap) fastfp/nmfp.py:77,
+ *                                                                     examples/run_nmfp.py:265-270
+ *     RN_container/CURN_container ._powerlaw / .get_phiinv            fastfp/nmfp.py:217-315
+ * so the entry points below are exactly what a ctypes binding of those calls needs
+ * (INTEGRATION.md shows that binding). Plain pointers and sizes only; no torch / CUDA types.
+ *
+ * Conventions
+ *  - all arithmetic and all arrays are IEEE float64 (reference fastfp/__init__.py:3);
+ *  - every function returns 0 on success or a negative FASTFP_ERR_* code; the message is
+ *    available from fastfp_last_error() (thread-local); nothing throws across the ABI;
+ *  - numerics never raise: NaN/Inf propagate as in the reference (singular M or Sigma,
+ *    f <= 0), SURVEY.md section 8(b);
+ *  - "host" pointers are ordinary process memory, "dev" pointers are CUDA device memory on
+ *    the pack's device; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *    Calls taking a stream are asynchronous on it unless they copy to host memory, in which
+ *    case they synchronise the stream before returning;
+ *  - the caller owns every input and output buffer; a pack owns only its own device memory.
+ */
+#ifndef FASTFP_B200_H
+#define FASTFP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FASTFP_OK 0
+#define FASTFP_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, ...) */
+#define FASTFP_ERR_CUDA (-2)        /* a CUDA runtime call failed */
+#define FASTFP_ERR_UNSUPPORTED (-3) /* shape outside what the kernels were built for */
+#define FASTFP_ERR_NOMEM (-4)
+
+/* memory-space flags for fastfp_fp_sweep / fastfp_nmfp_sweep */
+#define FASTFP_FREQS_ON_DEVICE 1
+#define FASTFP_OUT_ON_DEVICE 2
+#define FASTFP_PARAMS_ON_DEVICE 4
+
+typedef struct fastfp_pack fastfp_pack_t; /* opaque: device-resident packed pulsar array */
+
+const char* fastfp_last_error(void);
+int fastfp_version(void);
+int fastfp_device_count(void);
+
+/* ---- plain Fp ------------------------------------------------------------------------
+ * fastfp_pack_create: what FastFp.__init__ (fastfp/fastfp.py:39-45: toas, residuals) plus the
+ * (Nvecs, Ts, sigmas) lists of get_mats_fp (fastfp/utils.py:72-78) amount to: the P ragged
+ * per-pulsar arrays, copied from host memory and pre-reduced on the device into the packed
+ * layout the sweep kernel streams.
+ *   n[p]            number of TOAs           m[p]   number of basis columns of T_p
+ *   toas[p]         (n_p)   seconds          residuals[p] (n_p) seconds
+ *   Nvecs[p]        (n_p)   white-noise variances (diagonal N; utils.py:29-31)
+ *   Ts[p]           (n_p, m_p) row-major     sigmas[p]    (m_p, m_p) row-major, SPD
+ */
+int fastfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
+                       const double* const* toas, const double* const* residuals,
+                       const double* const* Nvecs, const double* const* Ts,
+                       const double* const* sigmas, void* stream, fastfp_pack_t** out);
+
+/* fastfp_fp_sweep: jax.vmap(FastFp.calculate_Fp, in_axes=(0,None,None,None))(freqs, ...)
+ * (examples/run_fp.py:63-64; per-frequency body fastfp/fastfp.py:69-92).  out[f] = Fp(freqs[f]),
+ * the pulsar sum taken in pulsar order starting from 0 (fastfp.py:71,90). */
+int fastfp_fp_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F, double* out,
+                    int flags, void* stream);
+
+/* per-pulsar terms 0.5*N^T M^-1 N (fastfp.py:90 before the sum): terms[p*F + f]. Same flags. */
+int fastfp_fp_terms(const fastfp_pack_t* pack, const double* freqs, int64_t F, double* terms,
+                    int flags, void* stream);
+
+/* ---- noise-marginalised Fp -----------------------------------------------------------
+ * fastfp_nmfp_pack_create: NMFP.__init__ (fastfp/nmfp.py:45-51) plus the (TNTs, Nvecs, Ts)
+ * of get_mats_nmfp (fastfp/utils.py:97-101). Sigma_d = TNT + diag(phiinv_d) is formed per
+ * draw (nmfp.py:58-74). The phi layouts of nmfp.py:264-292 are [tm | (ecorr) | rn(+curn)]:
+ * the first m_fix[p] entries do not depend on the draw (phiinv_fix[p], length m_fix[p]);
+ * the remaining m_var[p] = m[p] - m_fix[p] entries come per draw.
+ */
+int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
+                            const double* const* toas, const double* const* residuals,
+                            const double* const* Nvecs, const double* const* Ts,
+                            const double* const* TNTs, const int64_t* m_fix,
+                            const double* const* phiinv_fix, void* stream,
+                            fastfp_pack_t** out);
+
+/* fastfp_nmfp_sweep: vmap_g(vmap_f(nmfp))(freqs, samples, ...) of examples/run_nmfp.py:265-270.
+ * phiinv_var: (D, sum_p m_var[p]) row-major, draw d / pulsar p / varying column k at
+ * d*ld + off_p + k with off_p = sum_{q<p} m_var[q] and ld = sum_p m_var[p].
+ * out: (D, F) row-major, draw-major like the reference. */
+int fastfp_nmfp_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F,
+                      const double* phiinv_var, int64_t D, double* out, int flags, void* stream);
+
+/* fastfp_powerlaw_phiinv: RN_container.get_phiinv for the varying block (nmfp.py:226-234,
+ * 247/275 CURN add, 305-315 reciprocal), for D draws and P pulsars at once, on the device.
+ *   Ffreqs[p]      (m_var[p]) repeat(k/Tspan,2) of pulsar p (host)
+ *   log10_A, gamma (D, P) row-major red-noise parameters
+ *   curn_Ffreqs    (ncurn) or NULL; curn_log10_A, curn_gamma (D) -- added onto the leading
+ *                  ncurn entries of every pulsar (nmfp.py:275)
+ *   phiinv_var     output, device memory, layout as fastfp_nmfp_sweep expects. */
+int fastfp_powerlaw_phiinv(const fastfp_pack_t* pack, const double* const* Ffreqs,
+                           const double* log10_A, const double* gamma, int64_t D,
+                           const double* curn_Ffreqs, int64_t ncurn, const double* curn_log10_A,
+                           const double* curn_gamma, double* phiinv_var_dev, void* stream);
+
+void fastfp_pack_destroy(fastfp_pack_t* pack);
+int64_t fastfp_pack_bytes(const fastfp_pack_t* pack);    /* device bytes held */
+int fastfp_pack_num_pulsars(const fastfp_pack_t* pack);
+int64_t fastfp_pack_mvar_total(const fastfp_pack_t* pack); /* sum_p m_var[p] (nmfp packs) */
+int64_t fastfp_kernel_launches(void); /* kernels launched by this library so far (process-wide) */
+
+/* ---- single inner product --------------------------------------------------------------
+ * fastfp_xcy: fastfp.utils.get_xCy (fastfp/utils.py:49-54) on the device: host arrays in,
+ * x^T C^-1 y out, general (LU, partial pivoting) Sigma solve like jnp.linalg.solve. */
+int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
+               const double* sigma, const double* x, const double* y, double* out, void* stream);
+
+/* ---- measurement helper ----------------------------------------------------------------
+ * fastfp_fp64_peak: times a dependent-chain-free DFMA loop (kind 0) or DMMA m8n8k4 loop
+ * (kind 1), or both interleaved (kind 2), on the device and returns TFLOP/s; bench.py uses
+ * kind 0 as the measured fp64-pipe denominator (MEASURED_PEAKS.json has no fp64 figure). */
+int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms);
+
+/* fastfp_debug_trace: profiling aid. Runs one plain-Fp sweep and returns the per-warp clock64()
+ * stamps of CTA 0 for its first 64 chunks: trace_host[(chunk*8 + warp)*4 + k], k = iteration
+ * start / between the two phases / before the barrier / after the barrier. */
+int fastfp_debug_trace(const fastfp_pack_t* pack, const double* freqs, int64_t F,
+                       long long* trace_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTFP_B200_H */
