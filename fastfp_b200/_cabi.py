@@ -59,7 +59,6 @@ SYMBOLS = {
          C.c_void_p, C.c_void_p],
     ),
     "fastfp_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
-    "fastfp_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 
@@ -303,14 +302,6 @@ def fp64_peak(kind: int = 0, iters: int = 20000, device: int = 0):
     tf, ms = C.c_double(), C.c_double()
     check(lib.fastfp_fp64_peak(device, kind, iters, C.byref(tf), C.byref(ms)))
     return tf.value, ms.value
-
-
-def debug_trace(pack: "Pack", freqs) -> np.ndarray:
-    """Per-warp clock stamps of CTA 0, shape (64, 8, 4) (profiling aid)."""
-    freqs = as_f64(freqs)
-    tr = np.zeros((64, 8, 4), dtype=np.int64)
-    check(load().fastfp_debug_trace(pack._h, _vp(freqs), freqs.shape[0], _vp(tr)))
-    return tr
 
 
 def kernel_launches() -> int:

@@ -110,7 +110,7 @@ static int pack_layout(fastfp_pack* pk, int P, const int64_t* n, const int64_t* 
   FFP_CUDA(cudaMalloc(&pk->d_info, sizeof(int) * P));
   FFP_CUDA(cudaMemset(pk->d_info, 0, sizeof(int) * P));
   FFP_CUDA(cudaDeviceGetAttribute(&pk->num_sms, cudaDevAttrMultiProcessorCount, pk->device));
-  const size_t slab_bytes = (size_t)2 * pk->num_sms * sweep_max_slab_doubles() * 8;
+  const size_t slab_bytes = (size_t)CTAS_PER_SM * pk->num_sms * sweep_max_slab_doubles() * 8;
   FFP_CUDA(cudaMalloc(&pk->d_slab, slab_bytes));
   FFP_CUDA(cudaMalloc(&pk->d_counter, sizeof(unsigned int)));
   pk->bytes = pk_off * 8 + L_off * 8 + (int64_t)sizeof(PulsarMeta) * P + (int64_t)slab_bytes;
@@ -391,29 +391,8 @@ int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const doubl
   return rc;
 }
 
-// profiling aid: run one sweep with per-warp clock stamps of CTA 0 ([64 chunks][8 warps][4]).
-int fastfp_debug_trace(const fastfp_pack_t* pk, const double* freqs, int64_t F, long long* trace_host) {
-  if (!pk || !freqs || F < 1 || !trace_host) { set_error("fastfp_debug_trace: invalid argument"); return FASTFP_ERR_INVALID; }
-  DeviceGuard g(pk->device);
-  double *df = nullptr, *dt = nullptr;
-  long long* dtr = nullptr;
-  const size_t nt = 64 * 8 * 4;
-  FFP_CUDA(cudaMalloc(&df, F * 8));
-  FFP_CUDA(cudaMalloc(&dt, (size_t)pk->P * F * 8));
-  FFP_CUDA(cudaMalloc(&dtr, nt * 8));
-  FFP_CUDA(cudaMemset(dtr, 0, nt * 8));
-  FFP_CUDA(cudaMemcpy(df, freqs, F * 8, cudaMemcpyHostToDevice));
-  int rc = launch_fp_sweep(pk, df, F, dt, 0, nullptr, dtr);
-  if (!rc) {
-    cudaError_t e = cudaMemcpy(trace_host, dtr, nt * 8, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = cuda_fail(e, "trace copy");
-  }
-  cudaFree(df); cudaFree(dt); cudaFree(dtr);
-  return rc;
-}
-
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms) {
-  if (!tflops || !ms || iters < 1 || kind < 0 || kind > 4) {
+  if (!tflops || !ms || iters < 1 || kind < 0 || kind > 11) {
     set_error("fastfp_fp64_peak: invalid argument");
     return FASTFP_ERR_INVALID;
   }

@@ -11,35 +11,56 @@
 namespace ffp {
 
 // ---- tiling constants of the sweep kernel -------------------------
-constexpr int NW = 4;          // warps per sweep CTA (two CTAs are resident per SM)
-constexpr int NT = NW * 32;    // threads per sweep CTA
-constexpr int GST = 2;         // G-tile ring depth (TMA bulk copies)
-constexpr int VST = 4;         // TOA-vector ring depth (t | 1/N | w)
+constexpr int NW = 8;          // consumer (MMA) warps per sweep CTA; as many producer (sincos) warps
+constexpr int NT = NW * 32;    // threads per role
+constexpr int NTHREADS = 2 * NT;  // threads per sweep CTA (one CTA per SM, 128 registers per thread)
+constexpr int CTAS_PER_SM = 1;
+constexpr int VST = 16;        // TOA-vector ring depth (t | 1/N | w; TMA -> producer)
 constexpr int FLUSH_TOAS = 512;  // level-1 accumulation block, in TOAs
 constexpr int MAX_M = 256;     // widest basis the sweep kernel handles
 
-// Sweep configuration.
-//   TM  rows of G per thread           TQ  frequencies per thread (2*TQ columns: sin, cos)
-//   WMW warps along the basis (row) direction, NW/WMW along frequency
-//   CI  TOAs per staged chunk
-template <int TM_, int TQ_, int WMW_, int CI_>
+// Sweep configuration. The contraction runs on the fp64 MMA path (mma.sync.m8n8k4.f64): a warp
+// owns NMBW row blocks (8 basis rows each) x NNB column blocks (8 columns = 4 frequencies x
+// {sin, cos}); WMW warps split the rows, NW/WMW warps split the frequencies of the tile.
+//   CI  TOAs per staged chunk (KB = CI/4 k-blocks)
+template <int NMBW_, int NNB_, int WMW_, int CI_>
 struct SweepCfg {
-  static constexpr int TM = TM_, TQ = TQ_, WMW = WMW_, CI = CI_;
+  static constexpr int NMBW = NMBW_, NNB = NNB_, WMW = WMW_, CI = CI_;
   static constexpr int WNW = NW / WMW;         // warps along frequency
-  static constexpr int KF = WNW * 8 * TQ;      // frequencies per CTA
-  static constexpr int MP = WMW * 4 * TM;      // padded basis width (rows of G)
-  static constexpr int SROW = 2 * KF;          // doubles per TOA row of the sin/cos tile
+  static constexpr int KF = WNW * NNB * 4;     // frequencies per CTA
+  static constexpr int NBT = KF / 4;           // column blocks per CTA tile
+  static constexpr int NMB = NMBW * WMW;       // row blocks
+  static constexpr int MP = 8 * NMB;           // padded basis width (rows of G)
+  static constexpr int KB = CI / 4;            // k-blocks (4 TOAs) per chunk
+  static constexpr int ST = CI * 2 * KF;       // doubles of one sin/cos tile: [KB][NBT][32]
   static constexpr int VEC = 3 * CI;           // doubles of the vector part: t | 1/N | w
-  static constexpr int GT = CI * MP;           // doubles of the G part: G[CI][MP]
+  static constexpr int GT = CI * MP;           // doubles of the G part: [KB][NMB][32] fragments
   static constexpr int PK = VEC + GT;          // doubles per packet
-  static constexpr int IG = NT / KF;           // TOA groups in the basis-building phase
-  static constexpr int IPT = CI / IG;          // TOAs per thread per chunk in that phase
-  static constexpr int NACC = TM * 2 * TQ;     // accumulators per thread
-  static constexpr int SLAB = (NACC + 5) * NT; // doubles of level-2 scratch per CTA
+  // basis phase: one warp store covers 8 frequencies x 4 TOAs; a thread keeps XW frequencies
+  static constexpr int NX = KF / 8;                       // groups of 8 frequencies
+  static constexpr int XW = NX >= NW ? NX / NW : 1;       // frequency groups per warp
+  static constexpr int KSPLIT = NX >= NW ? 1 : NW / NX;   // warps sharing one group split the k-blocks
+  static constexpr int KBW = KB / KSPLIT;                 // k-blocks per warp
+  static constexpr int NACC = 2 * NMBW * NNB;  // accumulators per thread
+  static constexpr int SLAB = (NACC + 5 * XW) * NT;  // doubles of level-2 scratch per CTA
   static constexpr int FLUSH = FLUSH_TOAS / CI;  // chunks per level-1 block
-  static constexpr size_t SMEM = (size_t)(2 * CI * SROW + GST * GT + VST * VEC) * 8 + 128;
-  static_assert(NT % KF == 0 && CI % IG == 0, "basis-phase mapping");
+  // ring depths: sin/cos tiles (producer -> consumer) and G tiles (TMA -> consumer), as deep as
+  // the shared-memory budget allows
+  static constexpr int SST = ST * 8 * 8 <= 140 * 1024 ? 8 : 4;
+  static constexpr int GBUDGET = 214 * 1024 - SST * ST * 8 - VST * VEC * 8;
+  static constexpr int GST = GBUDGET / (GT * 8) >= 8 ? 8 : (GBUDGET / (GT * 8) >= 2 ? GBUDGET / (GT * 8) : 2);
+  static constexpr int RED = KF * (3 * WMW + 5 * KSPLIT);  // doubles of epilogue reduction scratch
+  static constexpr size_t SMEM =
+      (size_t)(SST * ST + GST * GT + VST * VEC + KF + RED + 2 * (SST + GST + VST)) * 8 + 128;
+  static_assert(KB % KSPLIT == 0 && NX * KSPLIT >= NW, "basis-phase mapping");
 };
+
+// offset of G element (TOA il within its chunk, basis row j) inside a packet's G part:
+// fragment order [k-block][row block][lane], lane = (j%8)*4 + il%4 -- the A-operand layout of
+// mma.m8n8k4 (row = lane>>2, k = lane&3), so a warp's fragment load is 256 contiguous bytes.
+__host__ __device__ inline int g_frag_index(int il, int j, int nmb) {
+  return (((il >> 2) * nmb + (j >> 3)) << 5) + (((j & 7) << 2) | (il & 3));
+}
 
 // Per-pulsar descriptor, device-visible.
 struct PulsarMeta {
@@ -54,13 +75,12 @@ struct PulsarMeta {
 };
 
 struct KernelCfg {  // run-time mirror of SweepCfg's parameters
-  int tm, tq, wmw, ci;
-  int kf() const { return (NW / wmw) * 8 * tq; }
-  int mp() const { return wmw * 4 * tm; }
-  int slab() const { return (tm * 2 * tq + 5) * NT; }
+  int nmbw, nnb, wmw, ci;
+  int kf() const { return (NW / wmw) * nnb * 4; }
+  int mp() const { return 8 * nmbw * wmw; }
   bool operator<(const KernelCfg& o) const {
-    if (tm != o.tm) return tm < o.tm;
-    if (tq != o.tq) return tq < o.tq;
+    if (nmbw != o.nmbw) return nmbw < o.nmbw;
+    if (nnb != o.nnb) return nnb < o.nnb;
     if (wmw != o.wmw) return wmw < o.wmw;
     return ci < o.ci;
   }
@@ -128,7 +148,7 @@ struct NmfpOut {      // stage-A outputs of the nmfp path (null for plain Fp)
   int mvmax;
 };
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
-                    cudaStream_t st, const NmfpOut* nm = nullptr, long long* trace = nullptr);
+                    cudaStream_t st, const NmfpOut* nm = nullptr);
 int launch_reduce_terms(const double* d_terms, int P, int64_t F, double* d_out, cudaStream_t st);
 bool sweep_config(int m, KernelCfg* cfg);
 int sweep_max_slab_doubles();
@@ -169,8 +189,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);  // back off: polling shares the MIO queue with LDS
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -5,23 +5,19 @@
 
 namespace ffp {
 
-// Kernel configuration for a basis of width m. Wider bases put more warps
-// along the row direction and fewer frequencies in a tile; the shared-memory budget keeps two
-// CTAs resident per SM in every configuration.
+// Kernel configuration for a basis of width m. A consumer warp owns NMBW
+// blocks of 8 basis rows x NNB blocks of 4 frequencies; wider bases put more warps along the row
+// direction and fewer frequencies in a tile.
 bool sweep_config(int m, KernelCfg* c) {
   if (m < 1 || m > MAX_M) return false;
-  if (m <= 40) { *c = {(m + 3) / 4, 4, 1, 16}; return true; }
-  if (m <= 80) { *c = {(m + 7) / 8, 4, 2, 32}; return true; }
-  if (m <= 160) {
-    const int tm = (m + 15) / 16;
-    *c = {tm, 4, 4, tm <= 8 ? 32 : 16};
-    return true;
-  }
-  *c = {(m + 15) / 16, 2, 4, 16};
+  if (m <= 40) { *c = {(m + 7) / 8, 4, 1, 16}; return true; }    // 128 frequencies per CTA
+  if (m <= 80) { *c = {(m + 7) / 8, 2, 1, 32}; return true; }    // 64 frequencies per CTA
+  if (m <= 160) { *c = {(m + 15) / 16, 2, 2, 16}; return true; }  // 32 frequencies per CTA
+  *c = {(m + 31) / 32, 2, 4, 16};                                 // 16 frequencies per CTA
   return true;
 }
 
-int sweep_max_slab_doubles() { return (10 * 8 + 5) * NT; }  // NACC <= 80 in every configuration
+int sweep_max_slab_doubles() { return (40 + 10) * NT; }  // NACC + 5*XW <= 50 in every configuration
 
 // out[f] = sum over pulsars in pulsar order, starting from 0 (fastfp.py:71,90).
 __global__ void reduce_terms_kernel(const double* __restrict__ terms, int P, int64_t F,
@@ -34,7 +30,7 @@ __global__ void reduce_terms_kernel(const double* __restrict__ terms, int P, int
 }
 
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
-                    cudaStream_t st, const NmfpOut* nm, long long* trace) {
+                    cudaStream_t st, const NmfpOut* nm) {
   static const int dbg = getenv("FASTFP_DBG") ? atoi(getenv("FASTFP_DBG")) : 0;  // profiling only
   SweepArgs a{};
   a.packets = pk->d_packets;
@@ -47,13 +43,12 @@ int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, dou
   a.Z = nm ? nm->Z : nullptr;
   a.A = nm ? nm->A : nullptr;
   a.mvmax = nm ? nm->mvmax : 0;
-  a.trace = trace;
   a.dbg = dbg;
   for (const Group& g : pk->groups) {
     int rc;
-    if (g.cfg.tq == 2) rc = dispatch_sweep_wide(pk, g, a, nm != nullptr, st);
-    else if (g.cfg.wmw == 1) rc = dispatch_sweep_w1(pk, g, a, nm != nullptr, st);
-    else if (g.cfg.wmw == 2) rc = dispatch_sweep_w2(pk, g, a, nm != nullptr, st);
+    if (g.cfg.wmw == 4) rc = dispatch_sweep_wide(pk, g, a, nm != nullptr, st);
+    else if (g.cfg.wmw == 1 && g.cfg.nnb == 4) rc = dispatch_sweep_w1(pk, g, a, nm != nullptr, st);
+    else if (g.cfg.wmw == 1) rc = dispatch_sweep_w2(pk, g, a, nm != nullptr, st);
     else rc = dispatch_sweep_w4(pk, g, a, nm != nullptr, st);
     if (rc) return rc;
   }

@@ -1,19 +1,26 @@
-// The frequency-sweep kernel (v2): a persistent CTA of 4 warps takes (pulsar, frequency-tile)
-// work items from an atomic counter; two CTAs are resident per SM.
+// The frequency-sweep kernel: a persistent, warp-specialised CTA (8 producer + 8 consumer warps,
+// one CTA per SM) takes (pulsar, frequency-tile) work items from an atomic counter.
 //
 // Replaces the body of FastFp.calculate_Fp under jax.vmap (reference fastfp/fastfp.py:69-92,
 // examples/run_fp.py:63) -- and, with NMFP = true, the draw-independent part of
 // NMFP.calculate_nmfp (fastfp/nmfp.py:96-119) -- for a whole frequency tile at once:
 //
-//   for each chunk of CI TOAs (two TMA bulk copies: the vectors t | 1/N | w, and the tile G[CI][MP]):
-//     basis phase : each thread builds sin/cos of ((2*pi)*f)*t (fastfp.py:78-79 phase order, one
-//                   rounding per multiply) for its (frequency, TOA) pairs, stores the pairs into
-//                   the shared S tile and accumulates s N^-1 s, s N^-1 c, c N^-1 c, s.w, c.w
-//     contraction : Y[MP][2*KF] += G_chunk^T . S_chunk as a register-tiled fp64 outer-product loop
-//                   (TM x 2*TQ accumulators per thread)
-//   epilogue      : b = Y_s.Y_s, Y_s.Y_c, Y_c.Y_c; M = [[sNs-b_ss, sNc-b_sc],[.., cNc-b_cc]],
-//                   N = [s.w, c.w]; general 2x2 solve with partial pivoting (what
-//                   jnp.linalg.solve does at fastfp.py:90); term = 0.5 * N . M^-1 N.
+//   per chunk of CI TOAs
+//     TMA        : two bulk copies per chunk -- the TOA vectors t | 1/N | w (to the producers) and
+//                  the G tile in MMA-fragment order (to the consumers) -- through mbarrier rings
+//     producers  : build sin/cos of ((2*pi)*f)*t (fastfp.py:78-79 phase order, one rounding per
+//                  multiply) for their (frequency, TOA) pairs, store them into the shared S-tile
+//                  ring in MMA-fragment order, and accumulate s N^-1 s, s N^-1 c, c N^-1 c, s.w, c.w
+//     consumers  : Y[MP][2*KF] += G_chunk^T . S_chunk on the fp64 MMA path (mma.sync.m8n8k4.f64;
+//                  measured to share the DFMA pipe and its peak, but with one 8-byte operand load
+//                  per 128 FMAs instead of one per ~4)
+//   epilogue     : b = Y_s.Y_s, Y_s.Y_c, Y_c.Y_c; M = [[sNs-b_ss, sNc-b_sc],[.., cNc-b_cc]],
+//                  N = [s.w, c.w]; general 2x2 solve with partial pivoting (what jnp.linalg.solve
+//                  does at fastfp.py:90); term = 0.5 * N . M^-1 N.
+//
+// Producers and consumers are decoupled by full/empty mbarriers, so the dependent sincos chains of
+// the producers (four independent evaluations in flight per thread) interleave with the consumers'
+// MMAs on the shared fp64 pipe at run time.
 //
 // The f^(-1/3) prefactor of fastfp.py:78-79 scales N by a and M by a^2 and cancels exactly in
 // N^T M^-1 N; it is not applied (f <= 0 still yields NaN as in the reference).
@@ -42,222 +49,344 @@ struct SweepArgs {
   double* Z;              // nmfp: [P][ceil(F/32)][mvmax][64]
   double* A;              // nmfp: [P][ceil(F/32)][5][32]
   int mvmax;
-  long long* trace;
   int dbg;
 };
 
-template <class C, bool NMFP>
-__global__ void __launch_bounds__(NT, 2) fp_sweep_kernel(const SweepArgs ar) {
-  constexpr int TM = C::TM, TQ = C::TQ, CI = C::CI;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* Sbuf = reinterpret_cast<double*>(smem_raw);   // [2][CI][SROW]
-  double* Gring = Sbuf + 2 * CI * C::SROW;              // [GST][GT]
-  double* Vring = Gring + GST * C::GT;                  // [VST][VEC]
-  uint64_t* gbar = reinterpret_cast<uint64_t*>(Vring + VST * C::VEC);  // [GST]
-  uint64_t* vbar = gbar + GST;                                         // [VST]
-  __shared__ int s_work;
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // basis-phase mapping: thread <-> (frequency fl, TOA group ig)
-  const int fl = tid % C::KF, ig = tid / C::KF;
-  // contraction mapping: warp (wm, wn), lane (lm, ln)
-  const int wm = wid / C::WNW, wn = wid - wm * C::WNW;
-  const int lm = lane >> 3, ln = lane & 7;
-  const int aoff = wm * 4 * TM + lm;            // rows aoff + 4*r
-  const int boff = 2 * (wn * 8 * TQ + ln);      // (s,c) pair of frequency wn*8*TQ + ln + 8*q at +16*q
-  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + tid;
-  const bool basis_first = (wid & 1) == 0;
-  const bool tr = ar.trace != nullptr && blockIdx.x == 0 && lane == 0;
-
-  if (tid == 0) {
-    for (int s = 0; s < GST; ++s) mbar_init(&gbar[s], 1);
-    for (int s = 0; s < VST; ++s) mbar_init(&vbar[s], 1);
-    fence_barrier_init();
+// D(8x8) += A(8x4) . B(4x8), fp64. Lane l holds A[l>>2][l&3], B[l&3][l>>2], D[l>>2][2*(l&3)+{0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Shared-memory carve-up, identical for both roles.
+template <class C>
+struct SweepSmem {
+  double* Sring;   // [C::SST][KB][NBT][32]   sin/cos tiles, B-fragment order
+  double* Gring;   // [GST][KB][NMB][32]   G tiles, A-fragment order
+  double* Vring;   // [VST][VEC]           t | 1/N | w
+  double* fq;      // [KF]                 trial frequencies of the current tile
+  double* red;     // [RED]                epilogue reduction scratch
+  uint64_t *s_full, *s_empty, *g_full, *g_empty, *v_full, *v_empty;
+  __device__ explicit SweepSmem(unsigned char* raw) {
+    Sring = reinterpret_cast<double*>(raw);
+    Gring = Sring + C::SST * C::ST;
+    Vring = Gring + C::GST * C::GT;
+    fq = Vring + VST * C::VEC;
+    red = fq + C::KF;
+    s_full = reinterpret_cast<uint64_t*>(red + C::RED);
+    s_empty = s_full + C::SST;
+    g_full = s_empty + C::SST;
+    g_empty = g_full + C::GST;
+    v_full = g_empty + C::GST;
+    v_empty = v_full + VST;
   }
-  __syncthreads();
+};
 
-  uint32_t g = 0;  // chunks consumed by this CTA so far: ring stage / mbarrier parity bookkeeping
-  int nitem = 0;
+struct WorkItem {
+  int p, ft, nch;
+  const double* gpk;
+};
+
+// ---- producer role: sin/cos tiles + the five weighted sums -----------------------------------
+template <class C, bool NMFP>
+__device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>& sm, volatile int* s_work,
+                                              const int pw, const int lane) {
+  constexpr int CI = C::CI, XW = C::XW;
+  const int tidp = pw * 32 + lane;
+  const int bk = lane & 3, bf8 = lane >> 2;
+  const int bx0 = C::NX >= NW ? pw * XW : pw % C::NX;          // first group of 8 frequencies
+  const int bkb0 = C::NX >= NW ? 0 : (pw / C::NX) * C::KBW;    // first k-block
+  const int bsplit = C::NX >= NW ? 0 : pw / C::NX;
+  // element (frequency group x, k-block kb) -> S offset (kb*NBT + 2*x + (bf8>>2))*32 + 4*(bf8&3) + bk
+  const int sofs = (bf8 >> 2) * 32 + 4 * (bf8 & 3) + bk;
+  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + (size_t)C::NACC * NT + tidp;
+  uint32_t g = 0;
   for (;;) {
-    if (tid == 0) s_work = (int)atomicAdd(ar.counter, 1u);
-    __syncthreads();
-    const int w = s_work;
+    __syncthreads();  // B1: work item published
+    const int w = *s_work;
+    if (w >= ar.nwork) break;
+    const int gp = w / ar.ntile_f;
+    const PulsarMeta pm = ar.meta[ar.pidx[gp]];
+    const double* gpk = ar.packets + pm.pk_off;
+    const int nch = pm.nch;
+    auto issue_vec = [&](int c) {
+      const uint32_t k = g + (uint32_t)c;
+      uint64_t* b = &sm.v_full[k % VST];
+      mbar_expect_tx(b, C::VEC * 8);
+      tma_load_1d(sm.Vring + (k % VST) * C::VEC, gpk + (size_t)c * C::PK, C::VEC * 8, b);
+    };
+    if (pw == 0 && lane == 0)
+      for (int c = 0; c < VST - 1 && c < nch; ++c) issue_vec(c);
+    __syncthreads();  // B2: frequencies of the tile are in shared memory
+    double omega[XW];
+#pragma unroll
+    for (int xx = 0; xx < XW; ++xx)
+      omega[xx] = __dmul_rn(6.283185307179586, sm.fq[8 * (bx0 + xx) + bf8]);  // (2*pi)*f, rounded once
+    double s2[XW][5];
+#pragma unroll
+    for (int xx = 0; xx < XW; ++xx)
+#pragma unroll
+      for (int q = 0; q < 5; ++q) s2[xx][q] = 0.0;
+    bool flushed = false;
+
+    for (int c = 0; c < nch; ++c) {
+      const uint32_t k = g + (uint32_t)c;
+      if (pw == 0 && lane == 0 && c + VST - 2 < nch && c >= 1) {
+        if (k >= 2) mbar_wait(&sm.v_empty[(k - 2) % VST], ((k - 2) / VST) & 1u);
+        issue_vec(c + VST - 2);
+      }
+      mbar_wait(&sm.v_full[k % VST], (k / VST) & 1u);
+      if (k >= C::SST) mbar_wait(&sm.s_empty[k % C::SST], ((k / C::SST) - 1) & 1u);
+      const double* pk = sm.Vring + (k % VST) * C::VEC;
+      double* sb = sm.Sring + (k % C::SST) * C::ST + sofs;
+      bool big = false;
+      if (!(ar.dbg & 1))
+#pragma unroll
+      for (int kk = 0; kk < C::KBW; ++kk) {
+        const int kb = bkb0 + kk;
+        const int i = 4 * kb + bk;
+        const double t = pk[i];
+#pragma unroll
+        for (int xx = 0; xx < XW; ++xx) {
+          const double ph = __dmul_rn(omega[xx], t);  // ((2*pi)*f)*t, rounded once more
+          const bool ok = fabs(ph) <= FFP_SINCOS_MAX;
+          big |= !ok;
+          double s, cs;
+          sincos_cw(ok ? ph : 0.0, &s, &cs);
+          const double ni = ok ? pk[CI + i] : 0.0, wv = ok ? pk[2 * CI + i] : 0.0;
+          double* dst = sb + (kb * C::NBT + 2 * (bx0 + xx)) * 32;
+          dst[0] = s;
+          dst[16] = cs;
+          const double sn = s * ni, cn = cs * ni;
+          s2[xx][0] = fma(sn, s, s2[xx][0]);
+          s2[xx][1] = fma(sn, cs, s2[xx][1]);
+          s2[xx][2] = fma(cn, cs, s2[xx][2]);
+          s2[xx][3] = fma(s, wv, s2[xx][3]);
+          s2[xx][4] = fma(cs, wv, s2[xx][4]);
+        }
+      }
+      if (big) {  // cold: phases beyond the Cody-Waite range (or NaN/Inf) take the library path
+#pragma unroll 1
+        for (int e = 0; e < C::KBW * XW; ++e) {
+          const int kb = bkb0 + e / XW, xx = e % XW;
+          const int i = 4 * kb + bk;
+          const double om = __dmul_rn(6.283185307179586, sm.fq[8 * (bx0 + xx) + bf8]);
+          const double ph = __dmul_rn(om, pk[i]);
+          if (fabs(ph) <= FFP_SINCOS_MAX) continue;
+          double s, cs;
+          sincos(ph, &s, &cs);
+          const double ni = pk[CI + i], wv = pk[2 * CI + i];
+          double* dst = sb + (kb * C::NBT + 2 * (bx0 + xx)) * 32;
+          dst[0] = s;
+          dst[16] = cs;
+          const double sn = s * ni, cn = cs * ni;
+#pragma unroll
+          for (int x2 = 0; x2 < XW; ++x2)
+            if (x2 == xx) {
+              s2[x2][0] = fma(sn, s, s2[x2][0]);
+              s2[x2][1] = fma(sn, cs, s2[x2][1]);
+              s2[x2][2] = fma(cn, cs, s2[x2][2]);
+              s2[x2][3] = fma(s, wv, s2[x2][3]);
+              s2[x2][4] = fma(cs, wv, s2[x2][4]);
+            }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sm.s_full[k % C::SST]);
+        mbar_arrive(&sm.v_empty[k % VST]);
+      }
+      if ((c + 1) % C::FLUSH == 0 && c + 1 < nch && !(ar.dbg & 4)) {
+#pragma unroll
+        for (int xx = 0; xx < XW; ++xx)
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            double* a = sl + (size_t)(xx * 5 + q) * NT;
+            double v = s2[xx][q];
+            if (flushed) v += __ldcg(a);
+            __stcg(a, v);
+            s2[xx][q] = 0.0;
+          }
+        flushed = true;
+      }
+    }
+    g += (uint32_t)nch;
+    // scalar sums: level-2 totals, then across the 4 lanes that share a frequency
+#pragma unroll
+    for (int xx = 0; xx < XW; ++xx)
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        double v = s2[xx][q];
+        if (flushed) v += __ldcg(sl + (size_t)(xx * 5 + q) * NT);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        s2[xx][q] = v;
+      }
+    double* redA = sm.red + C::WMW * C::KF * 3;  // [KSPLIT][KF][5]
+    if (bk == 0) {
+#pragma unroll
+      for (int xx = 0; xx < XW; ++xx)
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+          redA[(bsplit * C::KF + 8 * (bx0 + xx) + bf8) * 5 + q] = s2[xx][q];
+    }
+    __syncthreads();  // B3: reductions published
+    __syncthreads();  // B4: tile finished
+  }
+}
+
+// ---- consumer role: the contraction and the epilogue -----------------------------------------
+template <class C, bool NMFP>
+__device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>& sm, volatile int* s_work,
+                                              const int cw, const int lane) {
+  constexpr int NMBW = C::NMBW, NNB = C::NNB;
+  const int tid = cw * 32 + lane;
+  const int wm = cw / C::WNW, wn = cw - wm * C::WNW;
+  const int bperm = 16 * ((lane >> 2) & 1) + 4 * (lane >> 3) + (lane & 3);  // B-fragment position
+  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + tid;
+  uint32_t g = 0;
+  for (;;) {
+    if (tid == 0) *s_work = (int)atomicAdd(ar.counter, 1u);
+    __syncthreads();  // B1
+    const int w = *s_work;
     if (w >= ar.nwork) break;
     const int gp = w / ar.ntile_f, ft = w - gp * ar.ntile_f;
     const int p = ar.pidx[gp];
     const PulsarMeta pm = ar.meta[p];
     const double* gpk = ar.packets + pm.pk_off;
     const int nch = pm.nch;
-    const int64_t fidx = (int64_t)ft * C::KF + fl;
-    const double fval = fidx < ar.F ? ar.freqs[fidx] : 1.0;
-    const double omega = __dmul_rn(6.283185307179586, fval);  // (2*pi)*f, rounded once
-
-    auto issue_vec = [&](int c) {
-      const uint32_t k = g + (uint32_t)c;
-      uint64_t* b = &vbar[k % VST];
-      mbar_expect_tx(b, C::VEC * 8);
-      tma_load_1d(Vring + (k % VST) * C::VEC, gpk + (size_t)c * C::PK, C::VEC * 8, b);
-    };
+    const int64_t f0 = (int64_t)ft * C::KF;
     auto issue_G = [&](int c) {
       const uint32_t k = g + (uint32_t)c;
-      uint64_t* b = &gbar[k % GST];
+      uint64_t* b = &sm.g_full[k % C::GST];
       mbar_expect_tx(b, C::GT * 8);
-      tma_load_1d(Gring + (k % GST) * C::GT, gpk + (size_t)c * C::PK + C::VEC, C::GT * 8, b);
+      tma_load_1d(sm.Gring + (k % C::GST) * C::GT, gpk + (size_t)c * C::PK + C::VEC, C::GT * 8, b);
     };
-    if (tid == 0) {
-      issue_vec(0);
-      if (nch > 1) issue_vec(1);
-      issue_G(0);
-    }
+    if (tid == 0)
+      for (int c = 0; c < C::GST - 1 && c < nch; ++c) issue_G(c);  // chunks 0 .. GST-2 in flight
+    if (tid < C::KF) sm.fq[tid] = f0 + tid < ar.F ? ar.freqs[f0 + tid] : 1.0;
+    __syncthreads();  // B2
 
-    double acc[TM][2 * TQ];
+    double acc[NMBW][NNB][2];
 #pragma unroll
-    for (int r = 0; r < TM; ++r)
+    for (int r = 0; r < NMBW; ++r)
 #pragma unroll
-      for (int q = 0; q < 2 * TQ; ++q) acc[r][q] = 0.0;
-    double s2[5] = {0, 0, 0, 0, 0};
+      for (int q = 0; q < NNB; ++q) acc[r][q][0] = acc[r][q][1] = 0.0;
     bool flushed = false;
 
-    auto build_basis = [&](int c) {
-      const uint32_t k = g + (uint32_t)c;
-      mbar_wait(&vbar[k % VST], (k / VST) & 1u);
-      const double* pk = Vring + (k % VST) * C::VEC;
-      double* sb = Sbuf + (c & 1) * CI * C::SROW;
-      double l0 = 0, l1 = 0, l2 = 0, l3 = 0, l4 = 0;
-      bool big = false;
-#pragma unroll 8
-      for (int kk = 0; kk < C::IPT; ++kk) {  // straight-line: the evaluations interleave
-        const int i = ig * C::IPT + kk;
-        const double ph = __dmul_rn(omega, pk[i]);  // ((2*pi)*f)*t, rounded once more
-        const bool ok = fabs(ph) <= FFP_SINCOS_MAX;
-        big |= !ok;
-        double s, cs;
-        sincos_cw(ok ? ph : 0.0, &s, &cs);
-        const double ni = ok ? pk[CI + i] : 0.0, wv = ok ? pk[2 * CI + i] : 0.0;
-        *reinterpret_cast<double2*>(sb + i * C::SROW + 2 * fl) = make_double2(s, cs);
-        const double sn = s * ni, cn = cs * ni;
-        l0 = fma(sn, s, l0);
-        l1 = fma(sn, cs, l1);
-        l2 = fma(cn, cs, l2);
-        l3 = fma(s, wv, l3);
-        l4 = fma(cs, wv, l4);
-      }
-      if (big) {  // cold: phases beyond the Cody-Waite range (or NaN/Inf) take the library path
-#pragma unroll 1
-        for (int kk = 0; kk < C::IPT; ++kk) {
-          const int i = ig * C::IPT + kk;
-          const double ph = __dmul_rn(omega, pk[i]);
-          if (fabs(ph) <= FFP_SINCOS_MAX) continue;
-          double s, cs;
-          sincos(ph, &s, &cs);
-          const double ni = pk[CI + i], wv = pk[2 * CI + i];
-          *reinterpret_cast<double2*>(sb + i * C::SROW + 2 * fl) = make_double2(s, cs);
-          const double sn = s * ni, cn = cs * ni;
-          l0 = fma(sn, s, l0);
-          l1 = fma(sn, cs, l1);
-          l2 = fma(cn, cs, l2);
-          l3 = fma(s, wv, l3);
-          l4 = fma(cs, wv, l4);
-        }
-      }
-      s2[0] += l0; s2[1] += l1; s2[2] += l2; s2[3] += l3; s2[4] += l4;
-    };
-
-    auto contract = [&](int c) {
-      const uint32_t k = g + (uint32_t)c;
-      mbar_wait(&gbar[k % GST], (k / GST) & 1u);
-      const double* gt = Gring + (k % GST) * C::GT + aoff;
-      const double* sb = Sbuf + (c & 1) * CI * C::SROW + boff;
-#pragma unroll 2
-      for (int i = 0; i < CI; ++i) {
-        double a[TM], b[2 * TQ];
+    // fragments of the next k-block -- also across chunk boundaries -- are fetched while the MMAs of
+    // the current one run
+    double a0[NMBW], b0[NNB];
+    {
+      const uint32_t k = g;
+      mbar_wait(&sm.g_full[k % C::GST], (k / C::GST) & 1u);
+      mbar_wait(&sm.s_full[k % C::SST], (k / C::SST) & 1u);
+      const double* gt = sm.Gring + (k % C::GST) * C::GT + (wm * NMBW) * 32 + lane;
+      const double* sb = sm.Sring + (k % C::SST) * C::ST + (wn * NNB) * 32 + bperm;
 #pragma unroll
-        for (int r = 0; r < TM; ++r) a[r] = gt[i * C::MP + 4 * r];
+      for (int r = 0; r < NMBW; ++r) a0[r] = gt[r * 32];
 #pragma unroll
-        for (int q = 0; q < TQ; ++q) {  // 8-byte loads: 1 shared-memory wavefront each
-          b[2 * q] = sb[i * C::SROW + 16 * q];
-          b[2 * q + 1] = sb[i * C::SROW + 16 * q + 1];
-        }
-#pragma unroll
-        for (int r = 0; r < TM; ++r)
-#pragma unroll
-          for (int q = 0; q < 2 * TQ; ++q) acc[r][q] = fma(a[r], b[q], acc[r][q]);
-      }
-    };
-
-    // fold the level-1 sums into the level-2 totals of this CTA's scratch slab
-    auto flush = [&]() {
-#pragma unroll
-      for (int r = 0; r < TM; ++r)
-#pragma unroll
-        for (int q = 0; q < 2 * TQ; ++q) {
-          double* a = sl + (size_t)(r * 2 * TQ + q) * NT;
-          double v = acc[r][q];
-          if (flushed) v += __ldcg(a);
-          __stcg(a, v);
-          acc[r][q] = 0.0;
-        }
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        double* a = sl + (size_t)(C::NACC + k) * NT;
-        double v = s2[k];
-        if (flushed) v += __ldcg(a);
-        __stcg(a, v);
-        s2[k] = 0.0;
-      }
-      flushed = true;
-    };
-
-    build_basis(0);
-    __syncthreads();
+      for (int q = 0; q < NNB; ++q) b0[q] = sb[q * 32];
+    }
     for (int c = 0; c < nch; ++c) {
-      if (tr && nitem == 0 && c < 64) ar.trace[(c * 8 + wid) * 4 + 0] = clock64();
-      if (tid == 0) {
-        if (c + 1 < nch) issue_G(c + 1);
-        if (c + 2 < nch) issue_vec(c + 2);
+      const uint32_t k = g + (uint32_t)c;
+      // the issuer refills the stage freed two chunks ago, so its wait practically never blocks
+      if (tid == 0 && c + C::GST - 2 < nch && c >= 1) {
+        if (k >= 2) mbar_wait(&sm.g_empty[(k - 2) % C::GST], ((k - 2) / C::GST) & 1u);
+        issue_G(c + C::GST - 2);
       }
-      if (basis_first) {
-        if (c + 1 < nch && !(ar.dbg & 1)) build_basis(c + 1);
-        if (tr && nitem == 0 && c < 64) ar.trace[(c * 8 + wid) * 4 + 1] = clock64();
-        if (!(ar.dbg & 2)) contract(c);
-      } else {
-        if (!(ar.dbg & 2)) contract(c);
-        if (tr && nitem == 0 && c < 64) ar.trace[(c * 8 + wid) * 4 + 1] = clock64();
-        if (c + 1 < nch && !(ar.dbg & 1)) build_basis(c + 1);
+      const double* gt = sm.Gring + (k % C::GST) * C::GT + (wm * NMBW) * 32 + lane;
+      const double* sb = sm.Sring + (k % C::SST) * C::ST + (wn * NNB) * 32 + bperm;
+#pragma unroll
+      for (int kb = 0; kb < C::KB; ++kb) {
+        double a1[NMBW], b1[NNB];
+        if (kb + 1 < C::KB) {
+#pragma unroll
+          for (int r = 0; r < NMBW; ++r) a1[r] = gt[((kb + 1) * C::NMB + r) * 32];
+#pragma unroll
+          for (int q = 0; q < NNB; ++q) b1[q] = sb[((kb + 1) * C::NBT + q) * 32];
+        } else if (c + 1 < nch) {
+          const uint32_t k1 = k + 1;
+          mbar_wait(&sm.g_full[k1 % C::GST], (k1 / C::GST) & 1u);
+          mbar_wait(&sm.s_full[k1 % C::SST], (k1 / C::SST) & 1u);
+          const double* gt1 = sm.Gring + (k1 % C::GST) * C::GT + (wm * NMBW) * 32 + lane;
+          const double* sb1 = sm.Sring + (k1 % C::SST) * C::ST + (wn * NNB) * 32 + bperm;
+#pragma unroll
+          for (int r = 0; r < NMBW; ++r) a1[r] = gt1[r * 32];
+#pragma unroll
+          for (int q = 0; q < NNB; ++q) b1[q] = sb1[q * 32];
+        } else {
+#pragma unroll
+          for (int r = 0; r < NMBW; ++r) a1[r] = 0.0;
+#pragma unroll
+          for (int q = 0; q < NNB; ++q) b1[q] = 0.0;
+        }
+        if (!(ar.dbg & 2)) {
+#pragma unroll
+          for (int r = 0; r < NMBW; ++r)
+#pragma unroll
+            for (int q = 0; q < NNB; ++q) dmma_m8n8k4(acc[r][q][0], acc[r][q][1], a0[r], b0[q]);
+        }
+#pragma unroll
+        for (int r = 0; r < NMBW; ++r) a0[r] = a1[r];
+#pragma unroll
+        for (int q = 0; q < NNB; ++q) b0[q] = b1[q];
       }
-      if ((c + 1) % C::FLUSH == 0 && c + 1 < nch && !(ar.dbg & 4)) flush();
-      if (tr && nitem == 0 && c < 64) ar.trace[(c * 8 + wid) * 4 + 2] = clock64();
-      __syncthreads();
-      if (tr && nitem == 0 && c < 64) ar.trace[(c * 8 + wid) * 4 + 3] = clock64();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sm.g_empty[k % C::GST]);
+        mbar_arrive(&sm.s_empty[k % C::SST]);
+      }
+      if ((c + 1) % C::FLUSH == 0 && c + 1 < nch && !(ar.dbg & 4)) {
+        // fold the level-1 sums into the level-2 totals of this CTA's scratch slab
+#pragma unroll
+        for (int r = 0; r < NMBW; ++r)
+#pragma unroll
+          for (int q = 0; q < NNB; ++q)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              double* a = sl + (size_t)((r * NNB + q) * 2 + e) * NT;
+              double v = acc[r][q][e];
+              if (flushed) v += __ldcg(a);
+              __stcg(a, v);
+              acc[r][q][e] = 0.0;
+            }
+        flushed = true;
+      }
     }
     g += (uint32_t)nch;
-    ++nitem;
 
     // ---- epilogue ------------------------------------------------------------------------
     if (flushed) {
 #pragma unroll
-      for (int r = 0; r < TM; ++r)
+      for (int r = 0; r < NMBW; ++r)
 #pragma unroll
-        for (int q = 0; q < 2 * TQ; ++q) acc[r][q] += __ldcg(sl + (size_t)(r * 2 * TQ + q) * NT);
+        for (int q = 0; q < NNB; ++q)
 #pragma unroll
-      for (int k = 0; k < 5; ++k) s2[k] += __ldcg(sl + (size_t)(C::NACC + k) * NT);
+          for (int e = 0; e < 2; ++e)
+            acc[r][q][e] += __ldcg(sl + (size_t)((r * NNB + q) * 2 + e) * NT);
     }
+    // this thread holds Y[row][freq] for rows 8*(wm*NMBW + r) + (lane>>2) and the tile frequencies
+    // 4*(wn*NNB + q) + (lane&3): [..][0] is the sin column, [..][1] the cos column
     const int mfix = NMFP ? pm.mfix : pm.mpad;  // rows below mfix enter the b-sums
-    double bs[TQ][3];
+    double* redB = sm.red;  // [WMW][KF][3]
 #pragma unroll
-    for (int q = 0; q < TQ; ++q) {
+    for (int q = 0; q < NNB; ++q) {
       double pss = 0, psc = 0, pcc = 0;
 #pragma unroll
-      for (int r = 0; r < TM; ++r) {
-        const int j = aoff + 4 * r;
-        const double ys = acc[r][2 * q], yc = acc[r][2 * q + 1];
+      for (int r = 0; r < NMBW; ++r) {
+        const int j = 8 * (wm * NMBW + r) + (lane >> 2);
+        const double ys = acc[r][q][0], yc = acc[r][q][1];
         if (!NMFP || j < mfix) {
           pss = fma(ys, ys, pss);
           psc = fma(ys, yc, psc);
           pcc = fma(yc, yc, pcc);
         } else if (j < pm.m) {
           // nmfp: rows of the per-draw block go out as z' (canonical 32-frequency tiles)
-          const int64_t f = (int64_t)ft * C::KF + wn * 8 * TQ + ln + 8 * q;
+          const int64_t f = f0 + 4 * (wn * NNB + q) + (lane & 3);
           if (f < ar.F) {
             const int64_t nt32 = (ar.F + 31) >> 5;
             double* z = ar.Z + (((size_t)p * nt32 + (f >> 5)) * ar.mvmax + (j - mfix)) * 64 + 2 * (f & 31);
@@ -265,36 +394,25 @@ __global__ void __launch_bounds__(NT, 2) fp_sweep_kernel(const SweepArgs ar) {
           }
         }
       }
-      bs[q][0] = pss; bs[q][1] = psc; bs[q][2] = pcc;
-    }
-#pragma unroll
-    for (int q = 0; q < TQ; ++q)
+      double v3[3] = {pss, psc, pcc};
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        double v = bs[q][k];
+        double v = v3[k];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        bs[q][k] = v;
-      }
-    double* redB = Sbuf;                            // [WMW][KF][3]
-    double* redA = Sbuf + C::WMW * C::KF * 3;       // [IG][KF][5]
-    if (lm == 0) {
-#pragma unroll
-      for (int q = 0; q < TQ; ++q) {
-        const int f2 = wn * 8 * TQ + ln + 8 * q;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) redB[(wm * C::KF + f2) * 3 + k] = bs[q][k];
+        if ((lane >> 2) == 0) redB[(wm * C::KF + 4 * (wn * NNB + q) + (lane & 3)) * 3 + k] = v;
       }
     }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) redA[(ig * C::KF + fl) * 5 + k] = s2[k];
-    __syncthreads();
+    __syncthreads();  // B3: reductions (consumer b-sums, producer scalar sums) published
+    const int64_t fidx = f0 + tid;
     if (tid < C::KF && fidx < ar.F) {
+      const double* redA = sm.red + C::WMW * C::KF * 3;  // [KSPLIT][KF][5]
       double b[3] = {0, 0, 0}, a[5] = {0, 0, 0, 0, 0};
       for (int w2 = 0; w2 < C::WMW; ++w2)
 #pragma unroll
         for (int k = 0; k < 3; ++k) b[k] += redB[(w2 * C::KF + tid) * 3 + k];
-      for (int g2 = 0; g2 < C::IG; ++g2)
+      for (int g2 = 0; g2 < C::KSPLIT; ++g2)
 #pragma unroll
         for (int k = 0; k < 5; ++k) a[k] += redA[(g2 * C::KF + tid) * 5 + k];
       if (NMFP) {
@@ -315,16 +433,36 @@ __global__ void __launch_bounds__(NT, 2) fp_sweep_kernel(const SweepArgs ar) {
           t0 = m01; m01 = m11; m11 = t0;
           t0 = n0; n0 = n1; n1 = t0;
         }
-        const double l = m10 / m00;
-        const double u = m11 - l * m01;
-        const double x1 = (n1 - l * n0) / u;
+        const double lq = m10 / m00;
+        const double u = m11 - lq * m01;
+        const double x1 = (n1 - lq * n0) / u;
         const double x0 = (n0 - m01 * x1) / m00;
         double val = 0.5 * (a[3] * x0 + a[4] * x1);
-        if (!(fval > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);
+        if (!(sm.fq[tid] > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);
         ar.terms[(size_t)p * ar.F + fidx] = val;
       }
     }
-    __syncthreads();  // reduction scratch (Sbuf) and s_work are reused by the next work item
+    __syncthreads();  // B4: fq, red and s_work are reused by the next work item
+  }
+}
+
+template <class C, bool NMFP>
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fp_sweep_kernel(const SweepArgs ar) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SweepSmem<C> sm(smem_raw);
+  __shared__ int s_work;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < C::SST; ++s) { mbar_init(&sm.s_full[s], NW); mbar_init(&sm.s_empty[s], NW); }
+    for (int s = 0; s < C::GST; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], NW); }
+    for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], NW); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (wid < NW) {
+    consumer_loop<C, NMFP>(ar, sm, &s_work, wid, lane);
+  } else {
+    producer_loop<C, NMFP>(ar, sm, &s_work, wid - NW, lane);
   }
 }
 
@@ -344,24 +482,24 @@ int launch_sweep_cfg(const fastfp_pack* pk, const Group& g, const SweepArgs& bas
   if (nwork > 0x7fffffffLL) { set_error("frequency batch too large for one launch"); return -1; }
   a.ntile_f = (int)ntile;
   a.nwork = (int)nwork;
-  const int64_t resident = 2LL * pk->num_sms;
+  const int64_t resident = (int64_t)CTAS_PER_SM * pk->num_sms;
   const unsigned grid = (unsigned)(nwork < resident ? nwork : resident);
   FFP_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
-  fp_sweep_kernel<C, NMFP><<<grid, NT, C::SMEM, st>>>(a);
+  fp_sweep_kernel<C, NMFP><<<grid, NTHREADS, C::SMEM, st>>>(a);
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
   return 0;
 }
 
-// one translation unit per WMW family instantiates these (compile time)
+// one translation unit per configuration family instantiates these (compile time)
 int dispatch_sweep_w1(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 int dispatch_sweep_w2(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 int dispatch_sweep_w4(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 int dispatch_sweep_wide(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 
-#define FFP_SWEEP_CASE(TMv, TQv, WMWv, CIv)                                                        \
-  if (g.cfg.tm == TMv && g.cfg.tq == TQv && g.cfg.wmw == WMWv && g.cfg.ci == CIv)                   \
-    return nmfp ? launch_sweep_cfg<SweepCfg<TMv, TQv, WMWv, CIv>, true>(pk, g, a, st)              \
-                : launch_sweep_cfg<SweepCfg<TMv, TQv, WMWv, CIv>, false>(pk, g, a, st);
+#define FFP_SWEEP_CASE(NMBWv, NNBv, WMWv, CIv)                                                     \
+  if (g.cfg.nmbw == NMBWv && g.cfg.nnb == NNBv && g.cfg.wmw == WMWv && g.cfg.ci == CIv)             \
+    return nmfp ? launch_sweep_cfg<SweepCfg<NMBWv, NNBv, WMWv, CIv>, true>(pk, g, a, st)           \
+                : launch_sweep_cfg<SweepCfg<NMBWv, NNBv, WMWv, CIv>, false>(pk, g, a, st);
 
 }  // namespace ffp

@@ -2,8 +2,7 @@
 #include "fp_sweep_kernel.cuh"
 namespace ffp {
 int dispatch_sweep_wide(const fastfp_pack* pk, const Group& g, const SweepArgs& a, bool nmfp, cudaStream_t st) {
-  FFP_SWEEP_CASE(11, 2, 4, 16) FFP_SWEEP_CASE(12, 2, 4, 16) FFP_SWEEP_CASE(13, 2, 4, 16)
-  FFP_SWEEP_CASE(14, 2, 4, 16) FFP_SWEEP_CASE(15, 2, 4, 16) FFP_SWEEP_CASE(16, 2, 4, 16)
+  FFP_SWEEP_CASE(6, 2, 4, 16) FFP_SWEEP_CASE(7, 2, 4, 16) FFP_SWEEP_CASE(8, 2, 4, 16)
   set_error("no sweep kernel for this configuration (wide)");
   return -3;
 }

@@ -1,6 +1,7 @@
 // fp64 pipe peak: the measured denominator for the sweep kernel's fp64 roofline
 // (MEASURED_PEAKS.json carries only HBM and bf16 figures). kind 0 = DFMA, kind 1 = DMMA m8n8k4.
 #include "ffp_internal.cuh"
+#include "ffp_sincos.cuh"
 
 namespace ffp {
 
@@ -109,6 +110,91 @@ __global__ void __launch_bounds__(128, 2) outer_peak_kernel(int iters, double se
   if (s == 12345.678) sink[0] = s;
 }
 
+// kind 5: one dependent DFMA chain per thread, one warp per SM sub-partition -> cycles per
+// dependent fp64 op. Returned through *tflops as cycles/op (ms is the kernel time).
+__global__ void __launch_bounds__(128) dfma_latency_kernel(int iters, double seed, double* sink, long long* cyc) {
+  double a = seed + threadIdx.x * 1e-3;
+  const double x = 1.0000001, y = 1e-9;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a = fma(a, x, y);
+  }
+  const long long t1 = clock64();
+  if (a == 12345.678) sink[0] = a;
+  if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+// kinds 6-8: the producers' per-element work (phase multiply, range check, sincos_cw, the five
+// weighted sums) with ILP = 1, 2, 4 independent evaluations per thread and 8 warps per SM.
+// Returned through *tflops as cycles per element per warp.
+template <int ILP>
+__global__ void __launch_bounds__(256) sincos_rate_kernel(int iters, double seed, double* sink, long long* cyc) {
+  double s2[5] = {0, 0, 0, 0, 0};
+  const double omega = 6.283185307179586 * (1e-8 + threadIdx.x * 1e-11);
+  double t = 4.6e9 + seed;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const double ph = __dmul_rn(omega, t + j * 86400.0);
+      const bool ok = fabs(ph) <= FFP_SINCOS_MAX;
+      double s, c;
+      sincos_cw(ok ? ph : 0.0, &s, &c);
+      const double ni = ok ? 1e13 : 0.0, wv = ok ? 1e6 : 0.0;
+      const double sn = s * ni, cn = c * ni;
+      s2[0] = fma(sn, s, s2[0]);
+      s2[1] = fma(sn, c, s2[1]);
+      s2[2] = fma(cn, c, s2[2]);
+      s2[3] = fma(s, wv, s2[3]);
+      s2[4] = fma(c, wv, s2[4]);
+    }
+    t += 1e6;
+  }
+  const long long t1 = clock64();
+  if (s2[0] + s2[1] + s2[2] + s2[3] + s2[4] == 12345.678) sink[0] = s2[0];
+  if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+// kinds 9-11: the consumer's MMA pattern in isolation -- NMBW x NNB accumulator tile per warp,
+// fragments re-read from shared memory for every k-block, WPS warps per SM sub-partition.
+template <int NMBW, int NNB>
+__global__ void __launch_bounds__(512) dmma_tile_kernel(int iters, double seed, double* sink) {
+  __shared__ double sh[(9 + 4) * 2 * 32];
+  for (int i = threadIdx.x; i < (9 + 4) * 2 * 32; i += blockDim.x) sh[i] = seed * 1e-3 + i * 1e-9;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  double acc[NMBW][NNB][2];
+#pragma unroll
+  for (int r = 0; r < NMBW; ++r)
+#pragma unroll
+    for (int q = 0; q < NNB; ++q) acc[r][q][0] = acc[r][q][1] = seed;
+  const volatile double* va = sh;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      double a[NMBW], b[NNB];
+#pragma unroll
+      for (int r = 0; r < NMBW; ++r) a[r] = va[(kb * 13 + r) * 32 + lane];
+#pragma unroll
+      for (int q = 0; q < NNB; ++q) b[q] = va[(kb * 13 + 9 + q) * 32 + lane];
+#pragma unroll
+      for (int r = 0; r < NMBW; ++r)
+#pragma unroll
+        for (int q = 0; q < NNB; ++q)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[r][q][0]), "+d"(acc[r][q][1])
+                       : "d"(a[r]), "d"(b[q]));
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int r = 0; r < NMBW; ++r)
+#pragma unroll
+    for (int q = 0; q < NNB; ++q) s += acc[r][q][0] + acc[r][q][1];
+  if (s == 12345.678) sink[0] = s;
+}
+
 int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
   int dev = 0, sms = 0;
   FFP_CUDA(cudaGetDevice(&dev));
@@ -120,11 +206,36 @@ int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
   FFP_CUDA(cudaEventCreate(&e1));
   const int grid = sms * 8;
   float best = 1e30f;
+  if (kind >= 5 && kind <= 8) {
+    long long* dc = nullptr;
+    long long hc = 0;
+    FFP_CUDA(cudaMalloc(&dc, 8));
+    for (int rep = 0; rep < 2; ++rep) {
+      FFP_CUDA(cudaEventRecord(e0));
+      if (kind == 5) dfma_latency_kernel<<<sms, 128>>>(iters, 1.0, sink, dc);
+      else if (kind == 6) sincos_rate_kernel<1><<<sms, 256>>>(iters, 1.0, sink, dc);
+      else if (kind == 7) sincos_rate_kernel<2><<<sms, 256>>>(iters, 1.0, sink, dc);
+      else sincos_rate_kernel<4><<<sms, 256>>>(iters, 1.0, sink, dc);
+      FFP_CUDA(cudaEventRecord(e1));
+      FFP_CUDA(cudaEventSynchronize(e1));
+      FFP_CUDA(cudaEventElapsedTime(&best, e0, e1));
+    }
+    FFP_CUDA(cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost));
+    g_launches += 2;
+    const double per = kind == 5 ? 16.0 * iters : (kind == 6 ? 1.0 : kind == 7 ? 2.0 : 4.0) * iters;
+    *tflops = (double)hc / per;
+    *ms_out = best;
+    cudaFree(dc); cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return 0;
+  }
   for (int rep = 0; rep < 4; ++rep) {
     FFP_CUDA(cudaEventRecord(e0));
     if (kind == 0) dfma_peak_kernel<<<grid, 256>>>(iters, 1.0, sink);
     else if (kind == 1) dmma_peak_kernel<<<grid, 256>>>(iters, 1.0, sink);
     else if (kind == 2) mixed_peak_kernel<<<grid, 256>>>(iters, 1.0, sink);
+    else if (kind == 9) dmma_tile_kernel<9, 2><<<sms, 256>>>(iters, 1.0, sink);    // 2 warps / sub-partition
+    else if (kind == 10) dmma_tile_kernel<9, 2><<<sms, 512>>>(iters, 1.0, sink);   // 4 warps / sub-partition
+    else if (kind == 11) dmma_tile_kernel<9, 4><<<sms, 128>>>(iters, 1.0, sink);   // 1 warp / sub-partition
     else if (kind == 3) outer_peak_kernel<false><<<sms * 2, 128>>>(iters, 1.0, sink);
     else outer_peak_kernel<true><<<sms * 2, 128>>>(iters, 1.0, sink);
     FFP_CUDA(cudaEventRecord(e1));
@@ -138,6 +249,9 @@ int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
   // DFMA: 16 fma/thread/iter; DMMA: 8 mma/warp/iter, 8*8*4 fma each
   const double fma_count = kind == 0   ? (double)grid * 256 * 16.0 * iters
                            : kind == 1 ? (double)grid * 8 * 8.0 * 256.0 * iters
+                           : kind == 9 ? (double)sms * 8 * 2 * 18 * 256.0 * iters
+                           : kind == 10 ? (double)sms * 16 * 2 * 18 * 256.0 * iters
+                           : kind == 11 ? (double)sms * 4 * 2 * 36 * 256.0 * iters
                            : kind == 2 ? (double)grid * (256 * 16.0 + 8 * 4.0 * 256.0) * iters
                                        : (double)sms * 2 * 128 * 144.0 * iters;
   *tflops = 2.0 * fma_count / (best * 1e-3) / 1e12;

@@ -1,7 +1,7 @@
 // One-time, frequency-independent per-pulsar work for the plain-Fp path:
 //   Sigma = L L^T,  G = L^-1 T^T N^-1  (m x n),  u_r = G r,  w = C^-1 r = N^-1 r - G^T u_r
 // and the packed, tile-contiguous layout the sweep kernel streams with one TMA bulk copy per
-// chunk: packet = [ t[CI] | 1/N[CI] | w[CI] | G[CI][MP] ]  (CI = 16 or 32 TOAs, per pulsar).
+// chunk: packet = [ t[CI] | 1/N[CI] | w[CI] | G in mma-fragment order (g_frag_index) ]  (CI = 16 or 32).
 //
 // The reference recomputes all of this for every frequency: T^T N^-1 x twice per get_xCy
 // (fastfp/utils.py:51-52) and an LU solve of Sigma per call (utils.py:54), six calls per
@@ -68,21 +68,23 @@ __global__ void build_packets_kernel(double* __restrict__ packets,
   pk[il] = valid ? toas[pm.raw_off + i] : 0.0;
   pk[CI + il] = ninv;
   pk[2 * CI + il] = 0.0;  // w, filled by w_kernel
-  double* grow = pk + 3 * CI + (size_t)il * mp;
+  double* gp = pk + 3 * CI;  // G part, fragment order
+  const int nmb = mp >> 3;
   if (!valid) {
-    for (int j = 0; j < mp; ++j) grow[j] = 0.0;
+    for (int j = 0; j < mp; ++j) gp[g_frag_index(il, j, nmb)] = 0.0;
     return;
   }
   const double* L = Lbuf + pm.L_off;
   const double* Ti = T + pm.T_off + (size_t)i * m;
-  // g lives in the packet row itself (read-back hits L1/L2); m is small.
+  double g[MAX_M];  // thread-local column of G (local memory; one-time work)
   for (int j = 0; j < m; ++j) {
     double acc = Ti[j] * ninv;
     const double* Lj = L + (size_t)j * m;
-    for (int k = 0; k < j; ++k) acc = fma(-Lj[k], grow[k], acc);
-    grow[j] = acc / Lj[j];
+    for (int k = 0; k < j; ++k) acc = fma(-Lj[k], g[k], acc);
+    g[j] = acc / Lj[j];
+    gp[g_frag_index(il, j, nmb)] = g[j];
   }
-  for (int j = m; j < mp; ++j) grow[j] = 0.0;
+  for (int j = m; j < mp; ++j) gp[g_frag_index(il, j, nmb)] = 0.0;
 }
 
 // u_r[j] = sum_i G[j][i] r_i. One CTA per pulsar, one warp per basis row at a time; lanes
@@ -97,7 +99,7 @@ __global__ void ur_kernel(const double* __restrict__ packets, const PulsarMeta* 
   for (int j = wid; j < pm.m; j += nw) {
     double acc = 0.0;
     for (int i = lane; i < pm.n; i += 32) {
-      const double g = pk0[(size_t)(i / CI) * pkw + 3 * CI + (size_t)(i % CI) * mp + j];
+      const double g = pk0[(size_t)(i / CI) * pkw + 3 * CI + g_frag_index(i % CI, j, mp >> 3)];
       acc = fma(g, res[pm.raw_off + i], acc);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -115,10 +117,10 @@ __global__ void w_kernel(double* __restrict__ packets, const PulsarMeta* __restr
   const int mp = pm.mpad, pkw = CI * (3 + mp);
   double* pk = packets + pm.pk_off + (size_t)(i / CI) * pkw;
   const int il = i % CI;
-  const double* grow = pk + 3 * CI + (size_t)il * mp;
+  const double* gp = pk + 3 * CI;
   const double* u = ur + (size_t)blockIdx.y * MAX_M;
   double acc = 0.0;
-  for (int j = 0; j < pm.m; ++j) acc = fma(grow[j], u[j], acc);
+  for (int j = 0; j < pm.m; ++j) acc = fma(gp[g_frag_index(il, j, mp >> 3)], u[j], acc);
   pk[2 * CI + il] = res[pm.raw_off + i] * pk[CI + il] - acc;
 }
 

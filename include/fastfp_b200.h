@@ -125,12 +125,6 @@ int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const doubl
  * kind 0 as the measured fp64-pipe denominator (MEASURED_PEAKS.json has no fp64 figure). */
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms);
 
-/* fastfp_debug_trace: profiling aid. Runs one plain-Fp sweep and returns the per-warp clock64()
- * stamps of CTA 0 for its first 64 chunks: trace_host[(chunk*8 + warp)*4 + k], k = iteration
- * start / between the two phases / before the barrier / after the barrier. */
-int fastfp_debug_trace(const fastfp_pack_t* pack, const double* freqs, int64_t F,
-                       long long* trace_host);
-
 #ifdef __cplusplus
 }
 #endif
