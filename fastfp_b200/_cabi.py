@@ -156,9 +156,9 @@ class Pack:
 
     @classmethod
     def create_fp(cls, toas, residuals, Nvecs, Ts, sigmas, device: int = 0, stream: int = 0) -> "Pack":
+        P, n, m, toas, residuals, Nvecs, Ts, sigmas = _check_lists(toas, residuals, Nvecs, Ts, sigmas, "sigmas")
         lib = load()
         require_device()
-        P, n, m, toas, residuals, Nvecs, Ts, sigmas = _check_lists(toas, residuals, Nvecs, Ts, sigmas, "sigmas")
         h = C.c_void_p()
         check(
             lib.fastfp_pack_create(
@@ -170,8 +170,6 @@ class Pack:
 
     @classmethod
     def create_nmfp(cls, toas, residuals, Nvecs, Ts, TNTs, m_fix, phiinv_fix, device: int = 0, stream: int = 0):
-        lib = load()
-        require_device()
         P, n, m, toas, residuals, Nvecs, Ts, TNTs = _check_lists(toas, residuals, Nvecs, Ts, TNTs, "TNTs")
         if len(m_fix) != P or len(phiinv_fix) != P:
             raise ValueError("m_fix and phiinv_fix must have one entry per pulsar")
@@ -183,6 +181,8 @@ class Pack:
             if a.shape[0] != int(m_fix[p]):
                 raise ValueError(f"pulsar {p}: phiinv_fix must have m_fix entries")
             pf.append(a if a.size else np.zeros(1))
+        lib = load()
+        require_device()
         h = C.c_void_p()
         check(
             lib.fastfp_nmfp_pack_create(
@@ -283,14 +283,14 @@ class Pack:
 
 
 def xcy(Nvec, T, sigma, x, y, device: int = 0, stream: int = 0) -> float:
-    lib = load()
-    require_device()
     Nvec, T, sigma, x, y = as_f64(Nvec), as_f64(T), as_f64(sigma), as_f64(x), as_f64(y)
     if T.ndim != 2:
         raise ValueError("get_xCy: T must be 2-D (ntoa, nbasis)")
     n, m = T.shape
     if Nvec.shape != (n,) or x.shape != (n,) or y.shape != (n,) or sigma.shape != (m, m):
         raise ValueError("get_xCy: shapes must be Nvec (n,), T (n,m), sigma (m,m), x (n,), y (n,)")
+    lib = load()
+    require_device()
     out = np.empty(1)
     check(lib.fastfp_xcy(device, n, m, _vp(Nvec), _vp(T), _vp(sigma), _vp(x), _vp(y), _vp(out), C.c_void_p(stream)))
     return float(out[0])
