@@ -39,8 +39,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "C2": dict(P=45, n=5000, F_per_gpu=10_000, cpu_sample=(45, 1024)),
-    "C4": dict(P=68, n=10_000, F_per_gpu=125_000, cpu_sample=(34, 512)),
+    "C2": dict(P=45, n=5000, F_per_gpu=10_000),
+    "C4": dict(P=68, n=10_000, F_per_gpu=125_000),
 }
 M_BASIS = 72
 
@@ -109,29 +109,40 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(wl, steps=1, warmup=0):
-    """The reference's CPU path (oracle port, batched like the vmapped XLA program) on a bounded
-    sample of the workload: `cpu_sample` = (pulsars, frequencies). Returns evals/s and metadata."""
+def cpu_reference_rate(wl, steps=1, warmup=0, target_s=12.0):
+    """The reference's CPU path (oracle port: the vmapped program's formulas, batched over
+    frequency, spread over all host cores) on a bounded sample of the workload. The sample (all
+    pulsars of the workload x a calibrated number of frequencies) is sized for ~target_s seconds
+    per step. Returns evals/s and metadata."""
     from fastfp_b200 import synth
     from oracle import fp_oracle
 
-    Ps, Fs = wl["cpu_sample"]
-    pta = synth.make_pta(Ps, wl["n"])
-    freqs = synth.fp_freqs(wl["F_per_gpu"])[:: max(1, wl["F_per_gpu"] // Fs)][:Fs]
-    args = (freqs, pta.toas, pta.residuals, pta.Nvecs, pta.Ts, pta.sigmas)
-    fp_oracle.fp_sweep(freqs[:32], *args[1:])  # BLAS warm-up
+    cores = os.cpu_count() or 1
+    pta = synth.make_pta(wl["P"], wl["n"])
+    grid = synth.fp_freqs(wl["F_per_gpu"])
+    common = (pta.toas, pta.residuals, pta.Nvecs, pta.Ts, pta.sigmas)
+    chunk = 64
+    fcal = max(chunk, chunk * (-(-cores // wl["P"])))  # enough pieces to occupy every core
+    fp_oracle.fp_sweep_mt(grid[:fcal], *common, workers=cores, chunk=chunk)  # warm-up
+    t0 = time.perf_counter()
+    fp_oracle.fp_sweep_mt(grid[:fcal], *common, workers=cores, chunk=chunk)
+    t_cal = time.perf_counter() - t0
+    Fs = int(min(wl["F_per_gpu"], max(fcal, fcal * target_s / max(t_cal, 1e-3))))
+    Fs = max(chunk, Fs // chunk * chunk)
+    freqs = grid[:: max(1, wl["F_per_gpu"] // Fs)][:Fs]
     for _ in range(warmup):
-        fp_oracle.fp_sweep(*args)
+        fp_oracle.fp_sweep_mt(freqs, *common, workers=cores, chunk=chunk)
     times = []
     for _ in range(max(1, steps)):
         t0 = time.perf_counter()
-        fp_oracle.fp_sweep(*args)
+        fp_oracle.fp_sweep_mt(freqs, *common, workers=cores, chunk=chunk)
         times.append(time.perf_counter() - t0)
-    evals = Ps * len(freqs)
+    evals = wl["P"] * len(freqs)
     return evals / statistics.median(times), {
-        "cores": os.cpu_count(), "kind": "port",
-        "sample": f"{Ps} pulsars x {wl['n']} TOAs x {len(freqs)} frequencies of the workload "
-                  f"({evals} evals per step, median of {max(1, steps)}), NumPy/SciPy oracle with threaded BLAS",
+        "cores": cores, "kind": "port",
+        "sample": f"{wl['P']} pulsars x {wl['n']} TOAs x {len(freqs)} of the {wl['F_per_gpu']} frequencies "
+                  f"({evals} evals per step, median of {max(1, steps)} step(s)); NumPy/SciPy restatement of the "
+                  f"reference formulas, (pulsar, 64-frequency) pieces on a {cores}-thread pool, 1 BLAS thread each",
         "ms_per_step": statistics.median(times) * 1e3,
     }
 
@@ -139,7 +150,8 @@ def cpu_reference_rate(wl, steps=1, warmup=0):
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    rate, meta = cpu_reference_rate(wl, steps=args.steps, warmup=min(args.warmup, 1))
+    rate, meta = cpu_reference_rate(wl, steps=args.steps, warmup=min(args.warmup, 1),
+                                    target_s=min(12.0, 120.0 / max(1, args.steps + min(args.warmup, 1))))
     line = {
         "impl": "reference", "metric": "Fp evals/sec (freqs x pulsars x draws)", "value": rate, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": meta["ms_per_step"],

@@ -129,6 +129,37 @@ def fp_sweep(freqs, toas, residuals, Nvecs, Ts, sigmas, chunk=256, per_pulsar=Fa
     return out
 
 
+def fp_sweep_mt(freqs, toas, residuals, Nvecs, Ts, sigmas, workers=None, chunk=128):
+    """:func:`fp_sweep` spread over the host cores: the (pulsar, frequency-chunk) pieces are
+    independent, so they run on a thread pool (NumPy releases the GIL in sin/cos/GEMM) with BLAS
+    limited to one thread per worker. Same arithmetic per piece as :func:`fp_sweep`; used as the
+    CPU baseline of bench.py (all host threads), not as a parity reference."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    from threadpoolctl import threadpool_limits
+
+    freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+    F, P = freqs.shape[0], len(toas)
+    workers = workers or os.cpu_count() or 1
+    terms = np.zeros((P, F))
+    tasks = [(p, lo) for lo in range(0, F, chunk) for p in range(P)]
+
+    def run(task):
+        p, lo = task
+        terms[p, lo : lo + chunk] = fp_sweep(
+            freqs[lo : lo + chunk], [toas[p]], [residuals[p]], [Nvecs[p]], [Ts[p]], [sigmas[p]], chunk=chunk
+        )
+
+    with threadpool_limits(limits=1):
+        with ThreadPoolExecutor(max_workers=min(workers, len(tasks))) as ex:
+            list(ex.map(run, tasks))
+    out = np.zeros(F)
+    for p in range(P):
+        out = out + terms[p]
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # red-noise containers                                           reference fastfp/nmfp.py:131-477
 # --------------------------------------------------------------------------------------
