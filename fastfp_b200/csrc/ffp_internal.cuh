@@ -111,6 +111,7 @@ struct fastfp_pack {
   int64_t bytes = 0;
   int64_t mvar_total = 0;
   int mvar_max = 0;
+  int mvpad = 0;           // nmfp: per-draw block width padded to the stage-B tile (32, 64 or 96)
   // nmfp only
   double* d_S0 = nullptr;  // [P][mvmax][mvmax] Schur complement of the fixed block (no phiinv)
   double* d_zr = nullptr;  // [P][mvmax]  z'_r
@@ -140,12 +141,13 @@ int cuda_fail(cudaError_t e, const char* what);
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------
 // precompute.cu
 int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_res,
-                         const double* d_Nvec, const double* d_T, cudaStream_t st);
+                         const double* d_Nvec, const double* d_T, cudaStream_t st,
+                         double* d_ur_keep = nullptr);  // d_ur_keep: [P][MAX_M], receives G r
 // fp_sweep*.cu
 struct NmfpOut {      // stage-A outputs of the nmfp path (null for plain Fp)
-  double* Z;          // [P][F][2][mvmax]  z'_s, z'_c
-  double* A;          // [P][F][5]         a_ss, a_sc, a_cc, a_sr, a_cr
-  int mvmax;
+  double* Z;          // [P][ceil(F/32)][mvpad/4][8][32]  z'_s, z'_c tiles in MMA B-fragment order
+  double* A;          // [P][ceil(F/32)][5][32]           a_ss, a_sc, a_cc, a_sr, a_cr
+  int mvmax;          // padded width of the per-draw block (multiple of 8)
 };
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
                     cudaStream_t st, const NmfpOut* nm = nullptr);

@@ -46,7 +46,7 @@ struct SweepArgs {
   double* terms;          // [P][F] (plain Fp)
   double* slab;           // level-2 scratch, SLAB doubles per CTA
   unsigned int* counter;  // work counter (zeroed before the launch)
-  double* Z;              // nmfp: [P][ceil(F/32)][mvmax][64]
+  double* Z;              // nmfp: [P][ceil(F/32)][mvmax/4][8][32] (B-fragment order, mvmax = padded)
   double* A;              // nmfp: [P][ceil(F/32)][5][32]
   int mvmax;
   int dbg;
@@ -388,9 +388,14 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
           // nmfp: rows of the per-draw block go out as z' (canonical 32-frequency tiles)
           const int64_t f = f0 + 4 * (wn * NNB + q) + (lane & 3);
           if (f < ar.F) {
+            // 32-frequency tile, MMA B-fragment order: k-block (row/4), column block (4 freqs), then
+            // position 16*sc + 4*(freq%4) + row%4 -- the layout stage B loads without conflicts
             const int64_t nt32 = (ar.F + 31) >> 5;
-            double* z = ar.Z + (((size_t)p * nt32 + (f >> 5)) * ar.mvmax + (j - mfix)) * 64 + 2 * (f & 31);
-            *reinterpret_cast<double2*>(z) = make_double2(ys, yc);
+            const int jr = j - mfix, fi = (int)(f & 31);
+            double* z = ar.Z + ((size_t)p * nt32 + (f >> 5)) * ((size_t)ar.mvmax * 64) +
+                        (size_t)(((jr >> 2) * 8 + (fi >> 2)) * 32 + 4 * (fi & 3) + (jr & 3));
+            z[0] = ys;
+            z[16] = yc;
           }
         }
       }

@@ -1,9 +1,452 @@
-// placeholder (nmfp path under construction)
+// Noise-marginalised Fp (reference fastfp/nmfp.py:57-119 under the double vmap of
+// examples/run_nmfp.py:265-270) on the device.
+//
+// The reference rebuilds Sigma_d = TNT + diag(phiinv_d) per draw (nmfp.py:58-74) and then redoes the
+// whole per-pulsar loop of calculate_Fp for every (draw, frequency). Only Sigma changes with the
+// draw, and of phiinv only the trailing "varying" block (the phi layouts of nmfp.py:264-292 are
+// [timing model 1e40 | fixed ECORR | red noise (+CURN)]). With the fixed columns X eliminated once
+// per pulsar (Schur complement),
+//     z^T Sigma_d^-1 z = |L_X^-1 z_X|^2 + z'^T S_d^-1 z',   S_d = S0 + diag(phiinv_var_d),
+//     z' = z_V - Sigma_VX Sigma_XX^-1 z_X,
+// so the work splits into
+//   stage A (fp_sweep_kernel<NMFP=true>, once per (pulsar, frequency)): the n-long contractions --
+//           the draw-independent parts a_ss, a_sc, a_cc, a_sr, a_cr and the vectors z'_s, z'_c;
+//   factor  (once per (pulsar, draw)): S_d = L L^T, L^-1 in MMA-fragment order, v = L^-1 z'_r;
+//   stage B (once per (pulsar, draw, frequency)): u = L^-1 z' for 32 frequencies at a time on the
+//           fp64 MMA path, the five m_var-long reductions, the 2x2 solve and the pulsar sum.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "../../include/fastfp_b200.h"
 #include "ffp_internal.cuh"
+
 namespace ffp {
-int nmfp_pack_finish(fastfp_pack*, const double*, const double*, const double*, const double*,
-                     const double*, const double*, cudaStream_t) { set_error("nmfp not built yet"); return FASTFP_ERR_UNSUPPORTED; }
-int nmfp_sweep_impl(const fastfp_pack*, const double*, int64_t, const double*, int64_t, double*, cudaStream_t) { set_error("nmfp not built yet"); return FASTFP_ERR_UNSUPPORTED; }
-int powerlaw_phiinv_impl(const fastfp_pack*, const double* const*, const double*, const double*, int64_t, const double*, int64_t, const double*, const double*, double*, cudaStream_t) { set_error("nmfp not built yet"); return FASTFP_ERR_UNSUPPORTED; }
+
+constexpr int NB_DT = 8;      // draws per stage-B CTA
+constexpr int NB_LST = 3;     // L^-1 ring depth
+
+__host__ __device__ inline int linv_blocks(int nmbv) {  // blocks (kb, mb >= kb/2) of a lower-tri L^-1
+  int n = 0;
+  for (int kb = 0; kb < 2 * nmbv; ++kb) n += nmbv - kb / 2;
+  return n;
 }
+__host__ __device__ inline int linv_block_off(int nmbv, int kb) {
+  int n = 0;
+  for (int k = 0; k < kb; ++k) n += nmbv - k / 2;
+  return n;
+}
+
+// ---- pack construction -------------------------------------------------------------------------
+// L buffer <- TNT + diag(phiinv_fix) on the fixed columns (the per-draw part is added later)
+__global__ void nmfp_init_sigma_kernel(double* __restrict__ Lbuf, const PulsarMeta* __restrict__ meta,
+                                       const double* __restrict__ TNT, const double* __restrict__ pf) {
+  const PulsarMeta pm = meta[blockIdx.x];
+  const int m = pm.m;
+  for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+    const int i = idx / m, j = idx - i * m;
+    double v = TNT[pm.L_off + idx];
+    if (i == j && i < pm.mfix) v += pf[(size_t)blockIdx.x * MAX_M + i];
+    Lbuf[pm.L_off + idx] = v;
+  }
+}
+
+// S0[p] (padded to mvpad, identity on the padding) and z'_r[p] out of the partially factored matrix
+__global__ void nmfp_extract_kernel(const double* __restrict__ Lbuf, const PulsarMeta* __restrict__ meta,
+                                    const double* __restrict__ ur, double* __restrict__ S0,
+                                    double* __restrict__ zr, int mvpad) {
+  const PulsarMeta pm = meta[blockIdx.x];
+  const int m = pm.m, mf = pm.mfix, mv = pm.mvar;
+  const double* A = Lbuf + pm.L_off;
+  double* S = S0 + (size_t)blockIdx.x * mvpad * mvpad;
+  for (int idx = threadIdx.x; idx < mvpad * mvpad; idx += blockDim.x) {
+    const int i = idx / mvpad, j = idx - i * mvpad;
+    double v = i == j ? 1.0 : 0.0;
+    if (i < mv && j < mv) v = i >= j ? A[(size_t)(mf + i) * m + mf + j] : A[(size_t)(mf + j) * m + mf + i];
+    S[idx] = v;
+  }
+  for (int k = threadIdx.x; k < mvpad; k += blockDim.x)
+    zr[(size_t)blockIdx.x * mvpad + k] = k < mv ? ur[(size_t)blockIdx.x * MAX_M + mf + k] : 0.0;
+}
+
+int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res, const double* d_Nvec,
+                     const double* d_T, const double* d_TNT, const double* d_phiinv_fix, cudaStream_t st) {
+  const int P = pk->P;
+  if (pk->mvar_max < 1) { set_error("nmfp pack: every pulsar needs at least one per-draw column (m_fix < m)"); return FASTFP_ERR_INVALID; }
+  for (auto& pm : pk->meta)
+    if (pm.mvar < 1) { set_error("nmfp pack: every pulsar needs at least one per-draw column (m_fix < m)"); return FASTFP_ERR_INVALID; }
+  const int nmbv = pk->mvar_max <= 32 ? 4 : pk->mvar_max <= 64 ? 8 : pk->mvar_max <= 96 ? 12 : 0;
+  if (!nmbv) { set_error("nmfp pack: more than 96 per-draw columns (48 Fourier components) is not supported"); return FASTFP_ERR_UNSUPPORTED; }
+  pk->mvpad = 8 * nmbv;
+  nmfp_init_sigma_kernel<<<P, 256, 0, st>>>(pk->d_L, pk->d_meta, d_TNT, d_phiinv_fix);
+  g_launches += 1;
+  double* d_ur = nullptr;
+  FFP_CUDA(cudaMalloc(&d_ur, (size_t)P * MAX_M * sizeof(double)));
+  int rc = launch_fp_precompute(pk, d_toas, d_res, d_Nvec, d_T, st, d_ur);
+  if (!rc) {
+    cudaError_t e = cudaMalloc(&pk->d_S0, (size_t)P * pk->mvpad * pk->mvpad * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&pk->d_zr, (size_t)P * pk->mvpad * 8);
+    if (e != cudaSuccess) rc = cuda_fail(e, "nmfp pack allocation");
+  }
+  if (!rc) {
+    nmfp_extract_kernel<<<P, 256, 0, st>>>(pk->d_L, pk->d_meta, d_ur, pk->d_S0, pk->d_zr, pk->mvpad);
+    g_launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "nmfp_extract_kernel");
+    pk->bytes += (int64_t)P * pk->mvpad * (pk->mvpad + 1) * 8;
+  }
+  cudaFree(d_ur);
+  return rc;
+}
+
+// ---- RN_container.get_phiinv on the device ------------------------------------------------------
+// phi_k = f_k^(-gamma) * (10^log10_A)^2 / 12 / pi^2 * fyr^(gamma-3) * df_k, left to right
+// (nmfp.py:226-234); the CURN power law is added onto the leading entries (nmfp.py:247/275);
+// phiinv = 1/phi (nmfp.py:315).
+__device__ __forceinline__ double powerlaw_phi(double f, double df, double log10_A, double gamma) {
+  const double fyr = 1.0 / 31557600.0;
+  const double amp = pow(10.0, log10_A);
+  return pow(f, -gamma) * (amp * amp) / 12.0 / 9.869604401089358 * pow(fyr, gamma - 3.0) * df;
+}
+
+__global__ void powerlaw_phiinv_kernel(const PulsarMeta* __restrict__ meta, const double* __restrict__ Ff,
+                                       const double* __restrict__ dfv, const double* __restrict__ logA,
+                                       const double* __restrict__ gam, int P, const double* __restrict__ cF,
+                                       const double* __restrict__ cdf, int ncurn,
+                                       const double* __restrict__ cA, const double* __restrict__ cG,
+                                       double* __restrict__ out, int64_t ld) {
+  const int d = blockIdx.x, p = blockIdx.y;
+  const PulsarMeta pm = meta[p];
+  const double A = logA[(size_t)d * P + p], g = gam[(size_t)d * P + p];
+  for (int k = threadIdx.x; k < pm.mvar; k += blockDim.x) {
+    double phi = powerlaw_phi(Ff[pm.var_off + k], dfv[pm.var_off + k], A, g);
+    if (k < ncurn) phi += powerlaw_phi(cF[k], cdf[k], cA[d], cG[d]);
+    out[(size_t)d * ld + pm.var_off + k] = 1.0 / phi;
+  }
+}
+
+static void host_df(const double* Ff, int n, std::vector<double>& df) {
+  // df = repeat(diff(concatenate(([0], Ffreqs[::2]))), 2)   (nmfp.py:226, 233)
+  df.resize(n);
+  double prev = 0.0;
+  for (int k = 0; k < n; k += 2) {
+    const double d = Ff[k] - prev;
+    prev = Ff[k];
+    df[k] = d;
+    if (k + 1 < n) df[k + 1] = d;
+  }
+}
+
+int powerlaw_phiinv_impl(const fastfp_pack* pk, const double* const* Ffreqs, const double* log10_A,
+                         const double* gamma, int64_t D, const double* curn_Ffreqs, int64_t ncurn,
+                         const double* curn_log10_A, const double* curn_gamma, double* out, cudaStream_t st) {
+  const int P = pk->P;
+  const int64_t ld = pk->mvar_total;
+  std::vector<double> hf(ld), hdf(ld), tmp;
+  for (int p = 0; p < P; ++p) {
+    const PulsarMeta& pm = pk->meta[p];
+    if (!Ffreqs[p]) { set_error("fastfp_powerlaw_phiinv: null Ffreqs"); return FASTFP_ERR_INVALID; }
+    if (ncurn > pm.mvar) { set_error("fastfp_powerlaw_phiinv: more CURN entries than per-draw columns"); return FASTFP_ERR_INVALID; }
+    host_df(Ffreqs[p], pm.mvar, tmp);
+    for (int k = 0; k < pm.mvar; ++k) { hf[pm.var_off + k] = Ffreqs[p][k]; hdf[pm.var_off + k] = tmp[k]; }
+  }
+  std::vector<double> cdf;
+  if (ncurn > 0) host_df(curn_Ffreqs, (int)ncurn, cdf);
+  const size_t nA = (size_t)D * P;
+  const size_t total = 2 * ld + 2 * nA + 2 * ncurn + 2 * D;
+  double* d = nullptr;
+  FFP_CUDA(cudaMalloc(&d, total * 8));
+  double *dF = d, *dDf = dF + ld, *dA = dDf + ld, *dG = dA + nA, *dcF = dG + nA, *dcdf = dcF + ncurn,
+         *dcA = dcdf + ncurn, *dcG = dcA + D;
+  cudaError_t e = cudaMemcpyAsync(dF, hf.data(), ld * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dDf, hdf.data(), ld * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dA, log10_A, nA * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dG, gamma, nA * 8, cudaMemcpyHostToDevice, st);
+  if (ncurn > 0) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dcF, curn_Ffreqs, ncurn * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dcdf, cdf.data(), ncurn * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dcA, curn_log10_A, D * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dcG, curn_gamma, D * 8, cudaMemcpyHostToDevice, st);
+  }
+  int rc = 0;
+  if (e != cudaSuccess) rc = cuda_fail(e, "fastfp_powerlaw_phiinv upload");
+  if (!rc) {
+    dim3 grid((unsigned)D, P);
+    powerlaw_phiinv_kernel<<<grid, 64, 0, st>>>(pk->d_meta, dF, dDf, dA, dG, P, dcF, dcdf, (int)ncurn, dcA,
+                                                 dcG, out, ld);
+    g_launches += 1;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host staging vectors go out of scope
+    if (e != cudaSuccess) rc = cuda_fail(e, "powerlaw_phiinv_kernel");
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// ---- per-(pulsar, draw) factorisation -----------------------------------------------------------
+// S_d = S0 + diag(phiinv_var_d) = L L^T in shared memory; X = L^-1; v = X z'_r. X is written in the
+// A-fragment order of mma.m8n8k4 (lane = (row%8)*4 + k%4), blocks (kb, mb >= kb/2) only.
+template <int MV>
+__global__ void __launch_bounds__(128) nmfp_factor_kernel(const double* __restrict__ S0,
+                                                          const double* __restrict__ zr,
+                                                          const PulsarMeta* __restrict__ meta,
+                                                          const double* __restrict__ phiinv_var, int64_t ld,
+                                                          double* __restrict__ lf, int lfw) {
+  constexpr int NMBV = MV / 8, LD = MV + 1;
+  extern __shared__ double sm[];
+  double* A = sm;            // [MV][LD]  S_d -> L
+  double* X = sm + MV * LD;  // [MV][LD]  L^-1
+  const int p = blockIdx.x, d = blockIdx.y, tid = threadIdx.x;
+  const PulsarMeta pm = meta[p];
+  const double* S = S0 + (size_t)p * MV * MV;
+  const double* ph = phiinv_var + (size_t)d * ld + pm.var_off;
+  for (int idx = tid; idx < MV * MV; idx += blockDim.x) {
+    const int i = idx / MV, j = idx - i * MV;
+    double v = S[idx];
+    if (i == j && i < pm.mvar) v += ph[i];
+    A[i * LD + j] = v;
+    X[i * LD + j] = 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < MV; ++j) {  // right-looking Cholesky, lower
+    if (tid == 0) A[j * LD + j] = sqrt(A[j * LD + j]);
+    __syncthreads();
+    const double dj = A[j * LD + j];
+    for (int i = j + 1 + tid; i < MV; i += blockDim.x) A[i * LD + j] = A[i * LD + j] / dj;
+    __syncthreads();
+    const int cnt = MV - j - 1;
+    for (int idx = tid; idx < cnt * cnt; idx += blockDim.x) {
+      const int ii = idx / cnt, kk = idx - ii * cnt;
+      if (kk <= ii) {
+        const int i = j + 1 + ii, k = j + 1 + kk;
+        A[i * LD + k] = fma(-A[i * LD + j], A[k * LD + j], A[i * LD + k]);
+      }
+    }
+    __syncthreads();
+  }
+  // X = L^-1: thread c owns column c (forward substitution of e_c)
+  for (int c = tid; c < MV; c += blockDim.x) {
+    for (int i = c; i < MV; ++i) {
+      double acc = i == c ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) acc = fma(-A[i * LD + k], X[k * LD + c], acc);
+      X[i * LD + c] = acc / A[i * LD + i];
+    }
+  }
+  __syncthreads();
+  double* out = lf + ((size_t)d * gridDim.x + p) * lfw;
+  const int nblk = linv_blocks(NMBV);
+  for (int idx = tid; idx < nblk * 32; idx += blockDim.x) {
+    const int b = idx >> 5, l = idx & 31;
+    int kb = 0, rem = b;  // invert the block numbering
+    while (rem >= NMBV - kb / 2) { rem -= NMBV - kb / 2; ++kb; }
+    const int mb = kb / 2 + rem;
+    out[idx] = X[(8 * mb + (l >> 2)) * LD + 4 * kb + (l & 3)];
+  }
+  // v = X z'_r
+  const double* z = zr + (size_t)p * MV;
+  for (int i = tid; i < MV; i += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k <= i; ++k) acc = fma(X[i * LD + k], z[k], acc);
+    out[nblk * 32 + i] = acc;
+  }
+}
+
+// ---- stage B ------------------------------------------------------------------------------------
+struct StageBArgs {
+  const double* Z;       // [P][nt32][MV*64]   z' tiles (B-fragment order)
+  const double* A;       // [P][nt32][160]     a_ss | a_sc | a_cc | a_sr | a_cr, 32 frequencies each
+  const double* lf;      // [Db][P][lfw]       L^-1 fragments + v
+  const double* freqs;   // [F]
+  double* out;           // [D][F]  (this launch writes rows d0 .. d0+Db-1)
+  int64_t F, out_ld;
+  int P, nt32, Db, lfw;
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+template <int NMBV>
+__global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
+  constexpr int MV = 8 * NMBV, KBV = 2 * NMBV, ZT = MV * 64;
+  extern __shared__ __align__(128) unsigned char raw[];
+  double* Zb = reinterpret_cast<double*>(raw);       // [2][ZT]
+  double* Ab = Zb + 2 * ZT;                          // [2][160]
+  double* Lb = Ab + 2 * 160;                         // [NB_LST][lfw]
+  uint64_t* zbar = reinterpret_cast<uint64_t*>(Lb + NB_LST * ar.lfw);  // [2]
+  uint64_t* lbar = zbar + 2;                                            // [NB_LST]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int tile = blockIdx.x, d0 = blockIdx.y * NB_DT;
+  const int nd = min(NB_DT, ar.Db - d0);
+  const int bperm = 16 * ((lane >> 2) & 1) + 4 * (lane >> 3) + (lane & 3);
+  const int nblk = linv_blocks(NMBV);
+  const int fi = 4 * w + (lane & 3);                 // this lane group's frequency inside the tile
+  const int64_t f = (int64_t)tile * 32 + fi;
+  const double fval = f < ar.F ? ar.freqs[f] : 1.0;
+  if (tid == 0) {
+    mbar_init(&zbar[0], 1); mbar_init(&zbar[1], 1);
+    for (int s = 0; s < NB_LST; ++s) mbar_init(&lbar[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue_Z = [&](int p) {
+    uint64_t* b = &zbar[p & 1];
+    mbar_expect_tx(b, (ZT + 160) * 8);
+    tma_load_1d(Zb + (p & 1) * ZT, ar.Z + ((size_t)p * ar.nt32 + tile) * ZT, ZT * 8, b);
+    tma_load_1d(Ab + (p & 1) * 160, ar.A + ((size_t)p * ar.nt32 + tile) * 160, 160 * 8, b);
+  };
+  const int nit = ar.P * nd;
+  auto issue_L = [&](int it) {
+    const int p = it / nd, dl = it - p * nd;
+    uint64_t* b = &lbar[it % NB_LST];
+    mbar_expect_tx(b, ar.lfw * 8);
+    tma_load_1d(Lb + (it % NB_LST) * ar.lfw, ar.lf + ((size_t)(d0 + dl) * ar.P + p) * ar.lfw, ar.lfw * 8, b);
+  };
+  if (tid == 0) {
+    issue_Z(0);
+    issue_L(0);
+    if (nit > 1) issue_L(1);
+  }
+  double fpacc[NB_DT];
+#pragma unroll
+  for (int k = 0; k < NB_DT; ++k) fpacc[k] = 0.0;
+
+  for (int it = 0; it < nit; ++it) {
+    const int p = it / nd, dl = it - p * nd;
+    if (tid == 0) {
+      if (it + 2 < nit) issue_L(it + 2);                 // stage freed by iteration it-1
+      if (dl == 0 && p + 1 < ar.P) issue_Z(p + 1);       // buffer freed by pulsar p-1
+    }
+    if (dl == 0) mbar_wait(&zbar[p & 1], (p >> 1) & 1);
+    mbar_wait(&lbar[it % NB_LST], (it / NB_LST) & 1);
+    const double* zt = Zb + (p & 1) * ZT + w * 32 + bperm;
+    const double* lt = Lb + (it % NB_LST) * ar.lfw;
+    double acc[NMBV][2];
+#pragma unroll
+    for (int mb = 0; mb < NMBV; ++mb) acc[mb][0] = acc[mb][1] = 0.0;
+#pragma unroll
+    for (int kb = 0; kb < KBV; ++kb) {
+      const double b = zt[kb * 8 * 32];
+      const int off = linv_block_off(NMBV, kb);
+#pragma unroll
+      for (int mb = kb / 2; mb < NMBV; ++mb)
+        dmma884(acc[mb][0], acc[mb][1], lt[(off + mb - kb / 2) * 32 + lane], b);
+    }
+    // u = L^-1 z' for row 8*mb + (lane>>2), frequency fi: [0] = sin, [1] = cos
+    const double* v = lt + nblk * 32;
+    double r5[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int mb = 0; mb < NMBV; ++mb) {
+      const double us = acc[mb][0], uc = acc[mb][1], vv = v[8 * mb + (lane >> 2)];
+      r5[0] = fma(us, us, r5[0]);
+      r5[1] = fma(us, uc, r5[1]);
+      r5[2] = fma(uc, uc, r5[2]);
+      r5[3] = fma(us, vv, r5[3]);
+      r5[4] = fma(uc, vv, r5[4]);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      r5[k] += __shfl_xor_sync(0xffffffffu, r5[k], 4);
+      r5[k] += __shfl_xor_sync(0xffffffffu, r5[k], 8);
+      r5[k] += __shfl_xor_sync(0xffffffffu, r5[k], 16);
+    }
+    if (lane < 4) {
+      const double* a = Ab + (p & 1) * 160 + fi;
+      double m00 = a[0] - r5[0], m01 = a[32] - r5[1], m10 = m01, m11 = a[64] - r5[2];
+      const double N0 = a[96] - r5[3], N1 = a[128] - r5[4];
+      double n0 = N0, n1 = N1;
+      if (fabs(m10) > fabs(m00)) {  // LU with partial pivoting (jnp.linalg.solve, nmfp.py:117)
+        double t0 = m00; m00 = m10; m10 = t0;
+        t0 = m01; m01 = m11; m11 = t0;
+        t0 = n0; n0 = n1; n1 = t0;
+      }
+      const double lq = m10 / m00;
+      const double u = m11 - lq * m01;
+      const double x1 = (n1 - lq * n0) / u;
+      const double x0 = (n0 - m01 * x1) / m00;
+      const double term = 0.5 * (N0 * x0 + N1 * x1);
+#pragma unroll
+      for (int k = 0; k < NB_DT; ++k)
+        if (k == dl) fpacc[k] += term;  // pulsar sum in pulsar order, starting from 0 (nmfp.py:98,117)
+    }
+    __syncthreads();
+  }
+  if (lane < 4 && f < ar.F) {
+#pragma unroll
+    for (int k = 0; k < NB_DT; ++k)
+      if (k < nd) {
+        double val = fpacc[k];
+        if (!(fval > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);
+        ar.out[(size_t)(d0 + k) * ar.out_ld + f] = val;
+      }
+  }
+}
+
+template <int NMBV>
+static int run_factor_and_stageB(const fastfp_pack* pk, const double* d_phiinv, int64_t ld, int Db,
+                                 StageBArgs sb, double* d_lf, cudaStream_t st) {
+  constexpr int MV = 8 * NMBV;
+  const size_t fsm = (size_t)2 * MV * (MV + 1) * 8;
+  static bool attr_done[64] = {};
+  const size_t bsm = (size_t)(2 * MV * 64 + 2 * 160 + NB_LST * sb.lfw) * 8 + 64;
+  if (!attr_done[pk->device & 63]) {
+    FFP_CUDA(cudaFuncSetAttribute(nmfp_factor_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    FFP_CUDA(cudaFuncSetAttribute(nmfp_stageB_kernel<NMBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    attr_done[pk->device & 63] = true;
+  }
+  dim3 gf(pk->P, Db);
+  nmfp_factor_kernel<MV><<<gf, 128, fsm, st>>>(pk->d_S0, pk->d_zr, pk->d_meta, d_phiinv, ld, d_lf, sb.lfw);
+  dim3 gb(sb.nt32, (Db + NB_DT - 1) / NB_DT);
+  nmfp_stageB_kernel<NMBV><<<gb, 256, bsm, st>>>(sb);
+  g_launches += 2;
+  FFP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, const double* d_phiinv_var,
+                    int64_t D, double* d_out, cudaStream_t st) {
+  const int P = pk->P, MV = pk->mvpad, NMBV = MV / 8;
+  const int lfw = linv_blocks(NMBV) * 32 + MV;
+  // frequency batches bound the stage-A outputs, draw batches the L^-1 store (~1.5 GiB each)
+  const int64_t per_f32 = (int64_t)P * (MV * 64 + 160);
+  int64_t FB = std::max<int64_t>(32, ((1LL << 27) / std::max<int64_t>(1, per_f32)) * 32);
+  FB = std::min<int64_t>(FB, (F + 31) / 32 * 32);
+  const int64_t DB = std::max<int64_t>(NB_DT, std::min<int64_t>(D, ((3LL << 26) / ((int64_t)P * lfw)) / NB_DT * NB_DT));
+  const int64_t nt32_max = FB / 32;
+  const int64_t need = P * nt32_max * (int64_t)(MV * 64 + 160) + DB * P * lfw;
+  if (pk->scratch_cap < need) {
+    if (pk->d_scratch) cudaFree(pk->d_scratch);
+    pk->d_scratch = nullptr;
+    pk->scratch_cap = 0;
+    FFP_CUDA(cudaMalloc(&pk->d_scratch, (size_t)need * 8));
+    pk->scratch_cap = need;
+  }
+  double* dZ = pk->d_scratch;
+  double* dA = dZ + P * nt32_max * (int64_t)MV * 64;
+  double* dLf = dA + P * nt32_max * 160;
+  for (int64_t f0 = 0; f0 < F; f0 += FB) {
+    const int64_t Fb = std::min(FB, F - f0);
+    const int nt32 = (int)((Fb + 31) / 32);
+    // stage-A tiles are written sparsely (rows of narrower pulsars, the tail of the last tile): clear
+    FFP_CUDA(cudaMemsetAsync(dZ, 0, (size_t)P * nt32 * (MV * 64) * 8, st));
+    FFP_CUDA(cudaMemsetAsync(dA, 0, (size_t)P * nt32 * 160 * 8, st));
+    NmfpOut nm{dZ, dA, MV};
+    if (int rc = launch_fp_sweep(pk, d_freqs + f0, Fb, nullptr, st, &nm)) return rc;
+    for (int64_t dd = 0; dd < D; dd += DB) {
+      const int Db = (int)std::min(DB, D - dd);
+      StageBArgs sb{dZ, dA, dLf, d_freqs + f0, d_out + dd * F + f0, Fb, F, P, nt32, Db, lfw};
+      const double* ph = d_phiinv_var + dd * pk->mvar_total;
+      int rc;
+      if (NMBV == 4) rc = run_factor_and_stageB<4>(pk, ph, pk->mvar_total, Db, sb, dLf, st);
+      else if (NMBV == 8) rc = run_factor_and_stageB<8>(pk, ph, pk->mvar_total, Db, sb, dLf, st);
+      else rc = run_factor_and_stageB<12>(pk, ph, pk->mvar_total, Db, sb, dLf, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+}  // namespace ffp

@@ -13,16 +13,19 @@
 namespace ffp {
 
 // In-place lower Cholesky of the m x m matrix at Lbuf + L_off (row-major; the strictly upper
-// part is left untouched and never read). One CTA per pulsar. info[p] = j+1 if pivot j is
-// not positive (the factor then carries NaN, which propagates like the reference's
-// non-raising jnp.linalg.solve on a singular Sigma).
+// part is left untouched and never read), stopped after the first mfix columns. One CTA per
+// pulsar. For a plain-Fp pack mfix = m (full factor). For an nmfp pack the leading mfix x mfix
+// block becomes L_X, the lower-left block becomes Sigma_VX L_X^-T, and the trailing block is left
+// holding the Schur complement TNT_VV - Sigma_VX Sigma_XX^-1 Sigma_XV (lower part).
+// info[p] = j+1 if pivot j is not positive (the factor then carries NaN, which propagates like
+// the reference's non-raising jnp.linalg.solve on a singular Sigma).
 __global__ void chol_kernel(double* __restrict__ Lbuf, const PulsarMeta* __restrict__ meta,
                             int* __restrict__ info) {
   const PulsarMeta pm = meta[blockIdx.x];
   const int m = pm.m;
   double* A = Lbuf + pm.L_off;
   __shared__ double djj;
-  for (int j = 0; j < m; ++j) {
+  for (int j = 0; j < pm.mfix; ++j) {
     if (threadIdx.x == 0) {
       const double d = A[(size_t)j * m + j];
       if (!(d > 0.0) && info[blockIdx.x] == 0) info[blockIdx.x] = j + 1;
@@ -77,11 +80,15 @@ __global__ void build_packets_kernel(double* __restrict__ packets,
   const double* L = Lbuf + pm.L_off;
   const double* Ti = T + pm.T_off + (size_t)i * m;
   double g[MAX_M];  // thread-local column of G (local memory; one-time work)
+  // rows below mfix: g = L_X^-1 T_X^T / N (forward substitution); rows of the per-draw block
+  // (nmfp): g = T_V^T / N - (Sigma_VX L_X^-T) g_X, i.e. the same recurrence without the division
+  const int mfix = pm.mfix;
   for (int j = 0; j < m; ++j) {
     double acc = Ti[j] * ninv;
     const double* Lj = L + (size_t)j * m;
-    for (int k = 0; k < j; ++k) acc = fma(-Lj[k], g[k], acc);
-    g[j] = acc / Lj[j];
+    const int kend = j < mfix ? j : mfix;
+    for (int k = 0; k < kend; ++k) acc = fma(-Lj[k], g[k], acc);
+    g[j] = j < mfix ? acc / Lj[j] : acc;
     gp[g_frag_index(il, j, nmb)] = g[j];
   }
   for (int j = m; j < mp; ++j) gp[g_frag_index(il, j, nmb)] = 0.0;
@@ -107,7 +114,7 @@ __global__ void ur_kernel(const double* __restrict__ packets, const PulsarMeta* 
   }
 }
 
-// w_i = r_i / N_i - sum_j G[j][i] u_r[j]   (= (C^-1 r)_i)
+// w_i = r_i / N_i - sum_{j < mfix} G[j][i] u_r[j]   (= (C^-1 r)_i for a plain-Fp pack)
 __global__ void w_kernel(double* __restrict__ packets, const PulsarMeta* __restrict__ meta,
                          const double* __restrict__ res, const double* __restrict__ ur) {
   const PulsarMeta pm = meta[blockIdx.y];
@@ -120,17 +127,17 @@ __global__ void w_kernel(double* __restrict__ packets, const PulsarMeta* __restr
   const double* gp = pk + 3 * CI;
   const double* u = ur + (size_t)blockIdx.y * MAX_M;
   double acc = 0.0;
-  for (int j = 0; j < pm.m; ++j) acc = fma(gp[g_frag_index(il, j, mp >> 3)], u[j], acc);
+  for (int j = 0; j < pm.mfix; ++j) acc = fma(gp[g_frag_index(il, j, mp >> 3)], u[j], acc);
   pk[2 * CI + il] = res[pm.raw_off + i] * pk[CI + il] - acc;
 }
 
 int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_res,
-                         const double* d_Nvec, const double* d_T, cudaStream_t st) {
+                         const double* d_Nvec, const double* d_T, cudaStream_t st, double* d_ur_keep) {
   const int P = pk->P;
   int nmax = 0;
   for (auto& m : pk->meta) nmax = m.nch * m.ci > nmax ? m.nch * m.ci : nmax;
-  double* d_ur = nullptr;
-  FFP_CUDA(cudaMalloc(&d_ur, (size_t)P * MAX_M * sizeof(double)));
+  double* d_ur = d_ur_keep;
+  if (!d_ur) FFP_CUDA(cudaMalloc(&d_ur, (size_t)P * MAX_M * sizeof(double)));
   chol_kernel<<<P, 256, 0, st>>>(pk->d_L, pk->d_meta, pk->d_info);
   dim3 g1((nmax + 127) / 128, P);
   build_packets_kernel<<<g1, 128, 0, st>>>(pk->d_packets, pk->d_meta, pk->d_L, d_toas, d_Nvec, d_T);
@@ -139,7 +146,7 @@ int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_
   g_launches += 4;
   FFP_CUDA(cudaGetLastError());
   FFP_CUDA(cudaStreamSynchronize(st));
-  FFP_CUDA(cudaFree(d_ur));
+  if (!d_ur_keep) FFP_CUDA(cudaFree(d_ur));
   return 0;
 }
 

@@ -1,0 +1,150 @@
+"""GPU parity tests for the noise-marginalised path (NMFP.calculate_nmfp through the C ABI)."""
+import numpy as np
+import pytest
+
+import fastfp_b200
+from conftest import EPS, Psr
+from fastfp_b200 import NMFP, CURN_container, GPEcorr_container, RN_container, synth
+from oracle import fp_oracle as o
+from oracle import truth
+
+pytestmark = pytest.mark.gpu
+
+
+def _samples(g):
+    return {k[len("sample__"):]: g[k] for k in g.g.files if k.startswith("sample__")}
+
+
+def _tol(truth_vals, cond):
+    # the nmfp grid sits exactly on the red-noise Fourier frequencies (run_nmfp.py:247): the
+    # worst-conditioned points there are. 1e-10 relative plus the conditioning allowance.
+    return 1e-10 * np.abs(truth_vals) + 256 * EPS * cond
+
+
+def test_nmfp_matches_reference_goldens(golden):
+    g = golden("nmfp")
+    samples = _samples(g)
+    mats = (g.lst("Nvec"), g.lst("T"), g.lst("TNT"))
+    curn = CURN_container(g["Ffreqs_curn"])
+    sig_c = [RN_container(q, Ffreqs=g["Ffreqs"], add_curn=True, curn_container=curn) for q in g.psrs]
+    nm = NMFP(g.psrs, sig_c)
+    got = nm(g["freqs"], samples, *mats)
+    assert got.shape == g["ref_nmfp_curn"].shape  # (D, F), draw-major
+    tol = _tol(g["truth_nmfp_curn"], g["cond_curn"])
+    assert np.all(np.abs(got - g["truth_nmfp_curn"]) <= tol)
+    assert np.all(np.abs(got - g["ref_nmfp_curn"]) <= 2 * tol)
+    # the nested-vmap spelling of examples/run_nmfp.py:265-266
+    vf = fastfp_b200.vmap(nm, in_axes=(0, None, None, None, None))
+    vg = fastfp_b200.vmap(vf, in_axes=(None, 0, None, None, None))
+    np.testing.assert_array_equal(vg(g["freqs"], samples, *mats), got)
+    # without the common process
+    nm2 = NMFP(g.psrs, [RN_container(q, Ffreqs=g["Ffreqs"]) for q in g.psrs])
+    got2 = nm2(g["freqs"], samples, *mats)
+    assert np.all(np.abs(got2 - g["ref_nmfp_plain"]) <= 2 * tol + 1e-9 * np.abs(g["ref_nmfp_plain"]))
+
+
+def test_nmfp_batching_shapes(golden):
+    g = golden("nmfp")
+    samples = _samples(g)
+    mats = (g.lst("Nvec"), g.lst("T"), g.lst("TNT"))
+    nm = NMFP(g.psrs, [RN_container(q, Ffreqs=g["Ffreqs"]) for q in g.psrs])
+    full = nm(g["freqs"], samples, *mats)
+    pars1 = {k: v[1] for k, v in samples.items()}
+    row = nm(g["freqs"], pars1, *mats)
+    assert row.shape == (g["freqs"].shape[0],)
+    np.testing.assert_array_equal(row, full[1])
+    colv = nm(float(g["freqs"][2]), samples, *mats)
+    assert colv.shape == (int(g["D"]),)
+    np.testing.assert_array_equal(colv, full[:, 2])
+    one = nm(float(g["freqs"][2]), pars1, *mats)
+    assert np.ndim(one) == 0 and one == full[1, 2]
+
+
+def test_device_powerlaw_matches_host_containers(golden):
+    import torch
+
+    g = golden("nmfp")
+    samples = _samples(g)
+    curn = CURN_container(g["Ffreqs_curn"])
+    sigs = [RN_container(q, Ffreqs=g["Ffreqs"], add_curn=True, curn_container=curn) for q in g.psrs]
+    nm = NMFP(g.psrs, sigs)
+    pack = nm.prepare(g.lst("Nvec"), g.lst("T"), g.lst("TNT"))
+    D = int(g["D"])
+    A = np.stack([samples[s.rn_A_name] for s in sigs], axis=1)
+    G = np.stack([samples[s.rn_gam_name] for s in sigs], axis=1)
+    out = torch.empty((D, pack.mvar_total), dtype=torch.float64, device="cuda")
+    pack.powerlaw_phiinv([s.Ffreqs for s in sigs], A, G, curn.Ffreqs, samples["gw_log10_A"], samples["gw_gamma"],
+                         out.data_ptr())
+    torch.cuda.synchronize()
+    host = np.concatenate([s.get_phiinv(samples)[:, s.tm_weights.shape[0]:] for s in sigs], axis=1)
+    np.testing.assert_allclose(out.cpu().numpy(), host, rtol=4e-15)  # pow() differs from NumPy's by ulps
+
+
+def _ecorr_case(seed=11):
+    """A pulsar set whose basis carries GP-ECORR columns: T = [tm | epoch indicators | Fourier]."""
+    pta = synth.make_pta(3, [240, 320, 200], n_tm=[8, 10, 6], ncomps=30, seed=seed)
+    psrs, Ts, TNTs, sigs, phi_args = [], [], [], [], []
+    wn = {}
+    for p, q in enumerate(pta.psrs):
+        n, ntm = q.toas.size, pta.n_tm[p]
+        nep = n // 4
+        U = np.zeros((n, nep))
+        U[np.arange(nep * 4), np.repeat(np.arange(nep), 4)] = 1.0
+        T = np.concatenate((pta.Ts[p][:, :ntm], U, pta.Ts[p][:, ntm:]), axis=1)
+        TNT = T.T @ (T / pta.Nvecs[p][:, None])
+        flags = np.array(["X"] * n)
+        psr = Psr(q.toas, q.residuals, name=q.name, Mmat=np.zeros((n, ntm)), backend_flags=flags)
+        wn[f"{q.name}_basis_ecorr_X_log10_ecorr"] = -6.5 - 0.2 * p
+        ec = GPEcorr_container(psr, [np.ones(nep)], fix_wn_vals=wn)
+        sigs.append(RN_container(psr, Ffreqs=pta.Ffreqs, gp_ecorr=True, ecorr_container=ec))
+        phi_args.append(dict(psr_name=q.name, n_tm=ntm, Ffreqs=pta.Ffreqs, ecorr_phi_fixed=ec.get_phi({})))
+        psrs.append(psr); Ts.append(T); TNTs.append(0.5 * (TNT + TNT.T))
+    return pta, psrs, Ts, TNTs, sigs, phi_args
+
+
+def test_gp_ecorr_columns_are_eliminated_as_fixed_block():
+    pta, psrs, Ts, TNTs, sigs, phi_args = _ecorr_case()
+    D, F = 5, 40
+    samples = synth.draw_samples(pta, D)
+    freqs = synth.nmfp_freqs(F, pta.Tspan) * 1.013  # off the exact Fourier grid: well conditioned
+    nm = NMFP(psrs, sigs)
+    got = nm(freqs, samples, pta.Nvecs, Ts, TNTs)
+    toas, res = [q.toas for q in psrs], [q.residuals for q in psrs]
+    want = o.nmfp_sweep(freqs, samples, toas, res, pta.Nvecs, Ts, TNTs, phi_args)
+    assert got.shape == (D, F)
+    # truth for one draw
+    pars = {k: v[2] for k, v in samples.items()}
+    tt, cond = truth.fp_sweep_truth(freqs, toas, res, pta.Nvecs, Ts, o.get_sigmas(pars, TNTs, phi_args))
+    assert np.all(np.abs(got[2] - tt.sum(0).astype(float)) <= _tol(tt.sum(0).astype(float), cond.sum(0)))
+    assert np.abs(got / want - 1).max() < 1e-7
+
+
+@pytest.mark.parametrize("ncomps,P", [(10, 2), (30, 5), (45, 3)])
+def test_nmfp_against_oracle_shapes(ncomps, P):
+    pta = synth.make_pta(P, [300 + 57 * p for p in range(P)], n_tm=[6 + p for p in range(P)], ncomps=ncomps, seed=31)
+    D, F = 11, 45  # not multiples of the draw tile (8) or the frequency tile (32)
+    samples = synth.draw_samples(pta, D)
+    freqs = np.concatenate((synth.nmfp_freqs(5, pta.Tspan), synth.fp_freqs(F - 5)))
+    curn = CURN_container(np.repeat(np.arange(1, 6) / pta.Tspan, 2))
+    sigs = [RN_container(q, Ffreqs=pta.Ffreqs, add_curn=True, curn_container=curn) for q in pta.psrs]
+    got = NMFP(pta.psrs, sigs)(freqs, samples, pta.Nvecs, pta.Ts, pta.TNTs)
+    phi_args = [dict(psr_name=q.name, n_tm=pta.n_tm[p], Ffreqs=pta.Ffreqs, add_curn=True, curn_Ffreqs=curn.Ffreqs)
+                for p, q in enumerate(pta.psrs)]
+    for d in (0, D - 1):
+        pars = {k: v[d] for k, v in samples.items()}
+        sig = o.get_sigmas(pars, pta.TNTs, phi_args)
+        tt, cond = truth.fp_sweep_truth(freqs, pta.toas, pta.residuals, pta.Nvecs, pta.Ts, sig)
+        tv = tt.sum(0).astype(float)
+        assert np.all(np.abs(got[d] - tv) <= _tol(tv, cond.sum(0))), (ncomps, d)
+
+
+def test_nmfp_consistent_with_plain_fp():
+    """With the draw equal to the fixed noise values the two paths must agree (same Sigma)."""
+    pta = synth.make_pta(3, 400, n_tm=12, ncomps=30, seed=8, inc_cp=False)
+    freqs = synth.fp_freqs(50)
+    fp = fastfp_b200.FastFp(pta.psrs)(freqs, pta.Nvecs, pta.Ts, pta.sigmas)
+    sigs = [RN_container(q, Ffreqs=pta.Ffreqs) for q in pta.psrs]
+    nm = NMFP(pta.psrs, sigs)(freqs, pta.noise, pta.Nvecs, pta.Ts, pta.TNTs)
+    well = freqs > 40 / pta.Tspan
+    assert np.abs(nm[well] / fp[well] - 1).max() < 1e-9
+    assert np.abs(nm / fp - 1).max() < 1e-5
