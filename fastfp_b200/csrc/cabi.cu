@@ -1,5 +1,6 @@
 // extern "C" entry points of libfastfp_b200.so (declared in include/fastfp_b200.h).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 
@@ -60,7 +61,7 @@ struct Staging {
 };
 
 static int pack_layout(fastfp_pack* pk, int P, const int64_t* n, const int64_t* m,
-                       const int64_t* m_fix) {
+                       const int64_t* m_fix, const double* const* toas) {
   pk->P = P;
   pk->meta.resize(P);
   int64_t pk_off = 0, L_off = 0, raw_off = 0, T_off = 0;
@@ -94,9 +95,16 @@ static int pack_layout(fastfp_pack* pk, int P, const int64_t* n, const int64_t* 
       return FASTFP_ERR_INVALID;
     }
     pm.var_off = var_off;
+    pm.tabs_max = 0.0;
+    if (!toas[p]) { set_error("null toas"); return FASTFP_ERR_INVALID; }
+    for (int64_t i = 0; i < n[p]; ++i) {
+      const double a = std::fabs(toas[p][i]);
+      if (!(a <= 1.7e308)) { pm.tabs_max = INFINITY; break; }
+      if (a > pm.tabs_max) pm.tabs_max = a;
+    }
     var_off += pm.mvar;
     pk->mvar_max = std::max(pk->mvar_max, pm.mvar);
-    pk_off += (int64_t)pm.nch * pm.ci * (3 + pm.mpad);
+    pk_off += (int64_t)pm.nch * pm.ci * (4 + pm.mpad);
     L_off += (int64_t)pm.m * pm.m;
     raw_off += pm.n;
     T_off += (int64_t)pm.n * pm.m;
@@ -182,7 +190,7 @@ int fastfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
   cudaStream_t st = (cudaStream_t)stream;
   fastfp_pack* pk = new fastfp_pack();
   pk->device = device;
-  int rc = pack_layout(pk, P, n, m, nullptr);
+  int rc = pack_layout(pk, P, n, m, nullptr, toas);
   Staging sg;
   if (!rc) rc = upload_ragged(&sg.d_toas, toas, pk, 0, st);
   if (!rc) rc = upload_ragged(&sg.d_res, residuals, pk, 0, st);
@@ -212,7 +220,7 @@ int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* 
   fastfp_pack* pk = new fastfp_pack();
   pk->device = device;
   pk->nmfp = true;
-  int rc = pack_layout(pk, P, n, m, m_fix);
+  int rc = pack_layout(pk, P, n, m, m_fix, toas);
   Staging sg;
   double *d_TNT = nullptr, *d_pf = nullptr;
   if (!rc) rc = upload_ragged(&sg.d_toas, toas, pk, 0, st);
@@ -392,7 +400,7 @@ int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const doubl
 }
 
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms) {
-  if (!tflops || !ms || iters < 1 || kind < 0 || kind > 11) {
+  if (!tflops || !ms || iters < 1 || kind < 0 || kind > 12) {
     set_error("fastfp_fp64_peak: invalid argument");
     return FASTFP_ERR_INVALID;
   }

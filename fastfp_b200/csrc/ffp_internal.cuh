@@ -11,38 +11,43 @@
 namespace ffp {
 
 // ---- tiling constants of the sweep kernel -------------------------
-constexpr int NW = 8;          // consumer (MMA) warps per sweep CTA; as many producer (sincos) warps
-constexpr int NT = NW * 32;    // threads per role
-constexpr int NTHREADS = 2 * NT;  // threads per sweep CTA (one CTA per SM, 128 registers per thread)
+constexpr int NWC = 8;         // consumer (MMA) warps per sweep CTA: two per SM sub-partition
+constexpr int NWP = 16;        // producer (sincos) warps per sweep CTA: four per SM sub-partition
+constexpr int NTC = NWC * 32, NTP = NWP * 32;
+constexpr int NTHREADS = NTC + NTP;  // 768 threads per sweep CTA, one CTA per SM
 constexpr int CTAS_PER_SM = 1;
+constexpr int CONSUMER_REGS = 120, PRODUCER_REGS = 56;  // setmaxnreg split of the 768 x 80 pool
 constexpr int VST = 16;        // TOA-vector ring depth (t | 1/N | w; TMA -> producer)
 constexpr int FLUSH_TOAS = 512;  // level-1 accumulation block, in TOAs
 constexpr int MAX_M = 256;     // widest basis the sweep kernel handles
 
 // Sweep configuration. The contraction runs on the fp64 MMA path (mma.sync.m8n8k4.f64): a warp
 // owns NMBW row blocks (8 basis rows each) x NNB column blocks (8 columns = 4 frequencies x
-// {sin, cos}); WMW warps split the rows, NW/WMW warps split the frequencies of the tile.
+// {sin, cos}); WMW consumer warps split the rows, NWC/WMW split the frequencies of the tile.
 //   CI  TOAs per staged chunk (KB = CI/4 k-blocks)
 template <int NMBW_, int NNB_, int WMW_, int CI_>
 struct SweepCfg {
   static constexpr int NMBW = NMBW_, NNB = NNB_, WMW = WMW_, CI = CI_;
-  static constexpr int WNW = NW / WMW;         // warps along frequency
+  static constexpr int WNW = NWC / WMW;        // consumer warps along frequency
   static constexpr int KF = WNW * NNB * 4;     // frequencies per CTA
   static constexpr int NBT = KF / 4;           // column blocks per CTA tile
   static constexpr int NMB = NMBW * WMW;       // row blocks
   static constexpr int MP = 8 * NMB;           // padded basis width (rows of G)
   static constexpr int KB = CI / 4;            // k-blocks (4 TOAs) per chunk
   static constexpr int ST = CI * 2 * KF;       // doubles of one sin/cos tile: [KB][NBT][32]
-  static constexpr int VEC = 3 * CI;           // doubles of the vector part: t | 1/N | w
+  static constexpr int VEC = 4 * CI;           // doubles of the vector part: (t, 1/N, w, 0) per TOA
   static constexpr int GT = CI * MP;           // doubles of the G part: [KB][NMB][32] fragments
   static constexpr int PK = VEC + GT;          // doubles per packet
   // basis phase: one warp store covers 8 frequencies x 4 TOAs; a thread keeps XW frequencies
   static constexpr int NX = KF / 8;                       // groups of 8 frequencies
-  static constexpr int XW = NX >= NW ? NX / NW : 1;       // frequency groups per warp
-  static constexpr int KSPLIT = NX >= NW ? 1 : NW / NX;   // warps sharing one group split the k-blocks
-  static constexpr int KBW = KB / KSPLIT;                 // k-blocks per warp
+  static constexpr int XW = NX >= NWP ? NX / NWP : 1;      // frequency groups per producer warp
+  // producer warps sharing one group split its k-blocks; with few groups and few k-blocks the
+  // surplus warps stay idle (they still take part in the barrier protocol)
+  static constexpr int KSPLIT = NX >= NWP ? 1 : (NWP / NX < KB ? NWP / NX : KB);
+  static constexpr int KBW = KB / KSPLIT;                 // k-blocks per active producer warp
+  static constexpr int NACTIVE = NX >= NWP ? NWP : NX * KSPLIT;  // producer warps with work
   static constexpr int NACC = 2 * NMBW * NNB;  // accumulators per thread
-  static constexpr int SLAB = (NACC + 5 * XW) * NT;  // doubles of level-2 scratch per CTA
+  static constexpr int SLAB = NACC * NTC + 5 * XW * NTP;  // doubles of level-2 scratch per CTA
   static constexpr int FLUSH = FLUSH_TOAS / CI;  // chunks per level-1 block
   // ring depths: sin/cos tiles (producer -> consumer) and G tiles (TMA -> consumer), as deep as
   // the shared-memory budget allows
@@ -52,7 +57,8 @@ struct SweepCfg {
   static constexpr int RED = KF * (3 * WMW + 5 * KSPLIT);  // doubles of epilogue reduction scratch
   static constexpr size_t SMEM =
       (size_t)(SST * ST + GST * GT + VST * VEC + KF + RED + 2 * (SST + GST + VST)) * 8 + 128;
-  static_assert(KB % KSPLIT == 0 && NX * KSPLIT >= NW, "basis-phase mapping");
+  static_assert(KB % KSPLIT == 0 && NACTIVE <= NWP, "basis-phase mapping");
+  static_assert(GST >= 3, "the consumers prefetch across chunk boundaries: three G stages at least");
 };
 
 // offset of G element (TOA il within its chunk, basis row j) inside a packet's G part:
@@ -72,11 +78,12 @@ struct PulsarMeta {
   int32_t mfix, mvar;  // nmfp: leading draw-independent columns / trailing per-draw columns
   int32_t var_off;     // nmfp: offset of this pulsar's varying block in a phiinv_var row
   int32_t ci;          // TOAs per packet for this pulsar's kernel configuration
+  double tabs_max;     // max |TOA| (inf if any TOA is not finite): decides the sincos path per tile
 };
 
 struct KernelCfg {  // run-time mirror of SweepCfg's parameters
   int nmbw, nnb, wmw, ci;
-  int kf() const { return (NW / wmw) * nnb * 4; }
+  int kf() const { return (NWC / wmw) * nnb * 4; }
   int mp() const { return 8 * nmbw * wmw; }
   bool operator<(const KernelCfg& o) const {
     if (nmbw != o.nmbw) return nmbw < o.nmbw;

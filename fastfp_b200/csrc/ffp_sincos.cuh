@@ -64,14 +64,24 @@ FFP_HD void sincos_cw(double x, double* sp, double* cp) {
   pc = ffp_fma(z, pc, -1.38888888888741095749e-03);
   pc = ffp_fma(z, pc, 4.16666666666666019037e-02);
   const double c = ffp_fma(z, ffp_fma(z, pc, -0.5), 1.0);
-  // quadrant: k mod 4 = 0:(s,c) 1:(c,-s) 2:(-s,-c) 3:(-c,s)
+  // quadrant: k mod 4 = 0:(s,c) 1:(c,-s) 2:(-s,-c) 3:(-c,s); the sign flips are integer XORs on
+  // the high words (an fp64 negate + select would cost four more instructions per value)
   const bool swap = (q & 1) != 0;
-  double so = swap ? c : s;
-  double co = swap ? s : c;
-  if (q & 2) so = -so;
-  if ((q + 1) & 2) co = -co;
-  *sp = so;
-  *cp = co;
+  const double so = swap ? c : s;
+  const double co = swap ? s : c;
+  const uint32_t fs = ((uint32_t)q & 2u) << 30, fc = ((uint32_t)(q + 1) & 2u) << 30;
+#if defined(__CUDA_ARCH__)
+  *sp = __hiloint2double(__double2hiint(so) ^ (int)fs, __double2loint(so));
+  *cp = __hiloint2double(__double2hiint(co) ^ (int)fc, __double2loint(co));
+#else
+  uint64_t bs, bc;
+  std::memcpy(&bs, &so, 8);
+  std::memcpy(&bc, &co, 8);
+  bs ^= (uint64_t)fs << 32;
+  bc ^= (uint64_t)fc << 32;
+  std::memcpy(sp, &bs, 8);
+  std::memcpy(cp, &bc, 8);
+#endif
 }
 
 }  // namespace ffp

@@ -6,8 +6,8 @@
 namespace ffp {
 
 // Kernel configuration for a basis of width m. A consumer warp owns NMBW
-// blocks of 8 basis rows x NNB blocks of 4 frequencies; wider bases put more warps along the row
-// direction and fewer frequencies in a tile.
+// blocks of 8 basis rows x NNB blocks of 4 frequencies; wider bases put more consumer warps along
+// the row direction and fewer frequencies in a tile.
 bool sweep_config(int m, KernelCfg* c) {
   if (m < 1 || m > MAX_M) return false;
   if (m <= 40) { *c = {(m + 7) / 8, 4, 1, 16}; return true; }    // 128 frequencies per CTA
@@ -17,7 +17,7 @@ bool sweep_config(int m, KernelCfg* c) {
   return true;
 }
 
-int sweep_max_slab_doubles() { return (40 + 10) * NT; }  // NACC + 5*XW <= 50 in every configuration
+int sweep_max_slab_doubles() { return 40 * NTC + 10 * NTP; }  // NACC <= 80, XW <= 2 in every configuration
 
 // out[f] = sum over pulsars in pulsar order, starting from 0 (fastfp.py:71,90).
 __global__ void reduce_terms_kernel(const double* __restrict__ terms, int P, int64_t F,

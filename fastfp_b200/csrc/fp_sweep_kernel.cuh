@@ -1,4 +1,4 @@
-// The frequency-sweep kernel: a persistent, warp-specialised CTA (8 producer + 8 consumer warps,
+// The frequency-sweep kernel: a persistent, warp-specialised CTA (8 producer + 4 consumer warps,
 // one CTA per SM) takes (pulsar, frequency-tile) work items from an atomic counter.
 //
 // Replaces the body of FastFp.calculate_Fp under jax.vmap (reference fastfp/fastfp.py:69-92,
@@ -6,7 +6,7 @@
 // NMFP.calculate_nmfp (fastfp/nmfp.py:96-119) -- for a whole frequency tile at once:
 //
 //   per chunk of CI TOAs
-//     TMA        : two bulk copies per chunk -- the TOA vectors t | 1/N | w (to the producers) and
+//     TMA        : two bulk copies per chunk -- the TOA vectors (t, 1/N, w) (to the producers) and
 //                  the G tile in MMA-fragment order (to the consumers) -- through mbarrier rings
 //     producers  : build sin/cos of ((2*pi)*f)*t (fastfp.py:78-79 phase order, one rounding per
 //                  multiply) for their (frequency, TOA) pairs, store them into the shared S-tile
@@ -19,8 +19,10 @@
 //                  does at fastfp.py:90); term = 0.5 * N . M^-1 N.
 //
 // Producers and consumers are decoupled by full/empty mbarriers, so the dependent sincos chains of
-// the producers (four independent evaluations in flight per thread) interleave with the consumers'
-// MMAs on the shared fp64 pipe at run time.
+// the producers interleave with the consumers' MMAs on the shared fp64 pipe at run time. Each SM
+// sub-partition hosts one consumer warp and two producer warps (so the producers win most issue
+// arbitration rounds and never starve the MMA stream of S tiles); the register file is split with
+// setmaxnreg (consumers 216, producers 112 registers per thread).
 //
 // The f^(-1/3) prefactor of fastfp.py:78-79 scales N by a and M by a^2 and cancels exactly in
 // N^T M^-1 N; it is not applied (f <= 0 still yields NaN as in the reference).
@@ -61,6 +63,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+template <int R>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+}
+template <int R>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+}
 // Shared-memory carve-up, identical for both roles.
 template <class C>
 struct SweepSmem {
@@ -97,12 +107,13 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
   constexpr int CI = C::CI, XW = C::XW;
   const int tidp = pw * 32 + lane;
   const int bk = lane & 3, bf8 = lane >> 2;
-  const int bx0 = C::NX >= NW ? pw * XW : pw % C::NX;          // first group of 8 frequencies
-  const int bkb0 = C::NX >= NW ? 0 : (pw / C::NX) * C::KBW;    // first k-block
-  const int bsplit = C::NX >= NW ? 0 : pw / C::NX;
-  // element (frequency group x, k-block kb) -> S offset (kb*NBT + 2*x + (bf8>>2))*32 + 4*(bf8&3) + bk
-  const int sofs = (bf8 >> 2) * 32 + 4 * (bf8 & 3) + bk;
-  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + (size_t)C::NACC * NT + tidp;
+  const int bx0 = C::NX >= NWP ? pw * XW : pw % C::NX;         // first group of 8 frequencies
+  const int bkb0 = C::NX >= NWP ? 0 : (pw / C::NX) * C::KBW;   // first k-block
+  const int bsplit = C::NX >= NWP ? 0 : pw / C::NX;
+  // element (frequency group x, k-block kb) -> S offset (kb*NBT + 2*x + (bf8>>2))*32 + 8*(bf8&3) + 2*bk:
+  // the (sin, cos) pair of a (TOA, frequency) is adjacent, so it goes out as one 16-byte store
+  const int sofs = (bf8 >> 2) * 32 + 8 * (bf8 & 3) + 2 * bk;
+  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + (size_t)C::NACC * NTC + tidp;
   uint32_t g = 0;
   for (;;) {
     __syncthreads();  // B1: work item published
@@ -125,6 +136,10 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
 #pragma unroll
     for (int xx = 0; xx < XW; ++xx)
       omega[xx] = __dmul_rn(6.283185307179586, sm.fq[8 * (bx0 + xx) + bf8]);  // (2*pi)*f, rounded once
+    bool fast = true;  // warp-uniform in practice; any lane out of range sends its warp down the cold path
+#pragma unroll
+    for (int xx = 0; xx < XW; ++xx) fast = fast && (fabs(omega[xx]) * pm.tabs_max <= 0.999 * FFP_SINCOS_MAX);
+    fast = __all_sync(0xffffffffu, fast);
     double s2[XW][5];
 #pragma unroll
     for (int xx = 0; xx < XW; ++xx)
@@ -142,56 +157,53 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
       if (k >= C::SST) mbar_wait(&sm.s_empty[k % C::SST], ((k / C::SST) - 1) & 1u);
       const double* pk = sm.Vring + (k % VST) * C::VEC;
       double* sb = sm.Sring + (k % C::SST) * C::ST + sofs;
-      bool big = false;
-      if (!(ar.dbg & 1))
+      if (!(ar.dbg & 1) && pw < C::NACTIVE) {
+        if (fast) {
+          // straight-line: every phase of this tile is inside the Cody-Waite range (checked once per
+          // work item against the pulsar's largest |TOA|), so there is no per-element test
 #pragma unroll
-      for (int kk = 0; kk < C::KBW; ++kk) {
-        const int kb = bkb0 + kk;
-        const int i = 4 * kb + bk;
-        const double t = pk[i];
+          for (int kk = 0; kk < C::KBW; ++kk) {
+            const int kb = bkb0 + kk;
+            const int i = 4 * kb + bk;
+            const double2 tn = *reinterpret_cast<const double2*>(pk + 4 * i);  // (t, 1/N)
+            const double wv = pk[4 * i + 2];
 #pragma unroll
-        for (int xx = 0; xx < XW; ++xx) {
-          const double ph = __dmul_rn(omega[xx], t);  // ((2*pi)*f)*t, rounded once more
-          const bool ok = fabs(ph) <= FFP_SINCOS_MAX;
-          big |= !ok;
-          double s, cs;
-          sincos_cw(ok ? ph : 0.0, &s, &cs);
-          const double ni = ok ? pk[CI + i] : 0.0, wv = ok ? pk[2 * CI + i] : 0.0;
-          double* dst = sb + (kb * C::NBT + 2 * (bx0 + xx)) * 32;
-          dst[0] = s;
-          dst[16] = cs;
-          const double sn = s * ni, cn = cs * ni;
-          s2[xx][0] = fma(sn, s, s2[xx][0]);
-          s2[xx][1] = fma(sn, cs, s2[xx][1]);
-          s2[xx][2] = fma(cn, cs, s2[xx][2]);
-          s2[xx][3] = fma(s, wv, s2[xx][3]);
-          s2[xx][4] = fma(cs, wv, s2[xx][4]);
-        }
-      }
-      if (big) {  // cold: phases beyond the Cody-Waite range (or NaN/Inf) take the library path
-#pragma unroll 1
-        for (int e = 0; e < C::KBW * XW; ++e) {
-          const int kb = bkb0 + e / XW, xx = e % XW;
-          const int i = 4 * kb + bk;
-          const double om = __dmul_rn(6.283185307179586, sm.fq[8 * (bx0 + xx) + bf8]);
-          const double ph = __dmul_rn(om, pk[i]);
-          if (fabs(ph) <= FFP_SINCOS_MAX) continue;
-          double s, cs;
-          sincos(ph, &s, &cs);
-          const double ni = pk[CI + i], wv = pk[2 * CI + i];
-          double* dst = sb + (kb * C::NBT + 2 * (bx0 + xx)) * 32;
-          dst[0] = s;
-          dst[16] = cs;
-          const double sn = s * ni, cn = cs * ni;
-#pragma unroll
-          for (int x2 = 0; x2 < XW; ++x2)
-            if (x2 == xx) {
-              s2[x2][0] = fma(sn, s, s2[x2][0]);
-              s2[x2][1] = fma(sn, cs, s2[x2][1]);
-              s2[x2][2] = fma(cn, cs, s2[x2][2]);
-              s2[x2][3] = fma(s, wv, s2[x2][3]);
-              s2[x2][4] = fma(cs, wv, s2[x2][4]);
+            for (int xx = 0; xx < XW; ++xx) {
+              const double ph = __dmul_rn(omega[xx], tn.x);  // ((2*pi)*f)*t, rounded once more
+              double s, cs;
+              sincos_cw(ph, &s, &cs);
+              *reinterpret_cast<double2*>(sb + (kb * C::NBT + 2 * (bx0 + xx)) * 32) = make_double2(s, cs);
+              const double sn = s * tn.y, cn = cs * tn.y;
+              s2[xx][0] = fma(sn, s, s2[xx][0]);
+              s2[xx][1] = fma(sn, cs, s2[xx][1]);
+              s2[xx][2] = fma(cn, cs, s2[xx][2]);
+              s2[xx][3] = fma(s, wv, s2[xx][3]);
+              s2[xx][4] = fma(cs, wv, s2[xx][4]);
             }
+          }
+        } else {
+          // cold: some phase of this tile may exceed the Cody-Waite range (or is NaN/Inf): library sincos
+#pragma unroll 1
+          for (int e = 0; e < C::KBW * XW; ++e) {
+            const int kb = bkb0 + e / XW, xx = e % XW;
+            const int i = 4 * kb + bk;
+            const double om = __dmul_rn(6.283185307179586, sm.fq[8 * (bx0 + xx) + bf8]);
+            const double ph = __dmul_rn(om, pk[4 * i]);
+            double s, cs;
+            sincos(ph, &s, &cs);
+            const double ni = pk[4 * i + 1], wv = pk[4 * i + 2];
+            *reinterpret_cast<double2*>(sb + (kb * C::NBT + 2 * (bx0 + xx)) * 32) = make_double2(s, cs);
+            const double sn = s * ni, cn = cs * ni;
+#pragma unroll
+            for (int x2 = 0; x2 < XW; ++x2)
+              if (x2 == xx) {
+                s2[x2][0] = fma(sn, s, s2[x2][0]);
+                s2[x2][1] = fma(sn, cs, s2[x2][1]);
+                s2[x2][2] = fma(cn, cs, s2[x2][2]);
+                s2[x2][3] = fma(s, wv, s2[x2][3]);
+                s2[x2][4] = fma(cs, wv, s2[x2][4]);
+              }
+          }
         }
       }
       __syncwarp();
@@ -204,7 +216,7 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
         for (int xx = 0; xx < XW; ++xx)
 #pragma unroll
           for (int q = 0; q < 5; ++q) {
-            double* a = sl + (size_t)(xx * 5 + q) * NT;
+            double* a = sl + (size_t)(xx * 5 + q) * NTP;
             double v = s2[xx][q];
             if (flushed) v += __ldcg(a);
             __stcg(a, v);
@@ -220,13 +232,13 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
         double v = s2[xx][q];
-        if (flushed) v += __ldcg(sl + (size_t)(xx * 5 + q) * NT);
+        if (flushed) v += __ldcg(sl + (size_t)(xx * 5 + q) * NTP);
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         s2[xx][q] = v;
       }
     double* redA = sm.red + C::WMW * C::KF * 3;  // [KSPLIT][KF][5]
-    if (bk == 0) {
+    if (bk == 0 && pw < C::NACTIVE) {
 #pragma unroll
       for (int xx = 0; xx < XW; ++xx)
 #pragma unroll
@@ -245,7 +257,8 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
   constexpr int NMBW = C::NMBW, NNB = C::NNB;
   const int tid = cw * 32 + lane;
   const int wm = cw / C::WNW, wn = cw - wm * C::WNW;
-  const int bperm = 16 * ((lane >> 2) & 1) + 4 * (lane >> 3) + (lane & 3);  // B-fragment position
+  // B fragment: lane holds S[k = lane&3][n = lane>>2], n = 2*(freq%4) + {sin, cos}; stored at 8*(n>>1) + 2*k + (n&1)
+  const int bperm = 8 * (lane >> 3) + 2 * (lane & 3) + ((lane >> 2) & 1);
   double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + tid;
   uint32_t g = 0;
   for (;;) {
@@ -348,7 +361,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
           for (int q = 0; q < NNB; ++q)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              double* a = sl + (size_t)((r * NNB + q) * 2 + e) * NT;
+              double* a = sl + (size_t)((r * NNB + q) * 2 + e) * NTC;
               double v = acc[r][q][e];
               if (flushed) v += __ldcg(a);
               __stcg(a, v);
@@ -367,7 +380,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
         for (int q = 0; q < NNB; ++q)
 #pragma unroll
           for (int e = 0; e < 2; ++e)
-            acc[r][q][e] += __ldcg(sl + (size_t)((r * NNB + q) * 2 + e) * NT);
+            acc[r][q][e] += __ldcg(sl + (size_t)((r * NNB + q) * 2 + e) * NTC);
     }
     // this thread holds Y[row][freq] for rows 8*(wm*NMBW + r) + (lane>>2) and the tile frequencies
     // 4*(wn*NNB + q) + (lane&3): [..][0] is the sin column, [..][1] the cos column
@@ -458,16 +471,18 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fp_sweep_kernel(const S
   __shared__ int s_work;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < C::SST; ++s) { mbar_init(&sm.s_full[s], NW); mbar_init(&sm.s_empty[s], NW); }
-    for (int s = 0; s < C::GST; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], NW); }
-    for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], NW); }
+    for (int s = 0; s < C::SST; ++s) { mbar_init(&sm.s_full[s], NWP); mbar_init(&sm.s_empty[s], NWC); }
+    for (int s = 0; s < C::GST; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], NWC); }
+    for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], NWP); }
     fence_barrier_init();
   }
   __syncthreads();
-  if (wid < NW) {
+  if (wid < NWC) {
+    reg_alloc<CONSUMER_REGS>();
     consumer_loop<C, NMFP>(ar, sm, &s_work, wid, lane);
   } else {
-    producer_loop<C, NMFP>(ar, sm, &s_work, wid - NW, lane);
+    reg_dealloc<PRODUCER_REGS>();
+    producer_loop<C, NMFP>(ar, sm, &s_work, wid - NWC, lane);
   }
 }
 

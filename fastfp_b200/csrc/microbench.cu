@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) sincos_rate_kernel(int iters, double seed
 // kinds 9-11: the consumer's MMA pattern in isolation -- NMBW x NNB accumulator tile per warp,
 // fragments re-read from shared memory for every k-block, WPS warps per SM sub-partition.
 template <int NMBW, int NNB>
-__global__ void __launch_bounds__(512) dmma_tile_kernel(int iters, double seed, double* sink) {
+__global__ void __launch_bounds__(NMBW * NNB > 18 ? 128 : 512) dmma_tile_kernel(int iters, double seed, double* sink) {
   __shared__ double sh[(9 + 4) * 2 * 32];
   for (int i = threadIdx.x; i < (9 + 4) * 2 * 32; i += blockDim.x) sh[i] = seed * 1e-3 + i * 1e-9;
   __syncthreads();
@@ -192,6 +192,34 @@ __global__ void __launch_bounds__(512) dmma_tile_kernel(int iters, double seed, 
   for (int r = 0; r < NMBW; ++r)
 #pragma unroll
     for (int q = 0; q < NNB; ++q) s += acc[r][q][0] + acc[r][q][1];
+  if (s == 12345.678) sink[0] = s;
+}
+
+// kind 12: the large fp64 MMA shape m16n8k16 (sm_90+): same FMAs per 8x fewer instructions?
+__global__ void __launch_bounds__(256) dmma_16816_kernel(int iters, double seed, double* sink) {
+  double c[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[k][j] = seed + k + j;
+  double a[8], b[4];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1.0 + (threadIdx.x + k) * 1e-9;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) b[k] = 1e-3 * (k + 1);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+          "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+          : "+d"(c[k][0]), "+d"(c[k][1]), "+d"(c[k][2]), "+d"(c[k][3])
+          : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]),
+            "d"(b[1]), "d"(b[2]), "d"(b[3]));
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s += c[k][0] + c[k][1] + c[k][2] + c[k][3];
   if (s == 12345.678) sink[0] = s;
 }
 
@@ -236,6 +264,7 @@ int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
     else if (kind == 9) dmma_tile_kernel<9, 2><<<sms, 256>>>(iters, 1.0, sink);    // 2 warps / sub-partition
     else if (kind == 10) dmma_tile_kernel<9, 2><<<sms, 512>>>(iters, 1.0, sink);   // 4 warps / sub-partition
     else if (kind == 11) dmma_tile_kernel<9, 4><<<sms, 128>>>(iters, 1.0, sink);   // 1 warp / sub-partition
+    else if (kind == 12) dmma_16816_kernel<<<sms, 256>>>(iters, 1.0, sink);
     else if (kind == 3) outer_peak_kernel<false><<<sms * 2, 128>>>(iters, 1.0, sink);
     else outer_peak_kernel<true><<<sms * 2, 128>>>(iters, 1.0, sink);
     FFP_CUDA(cudaEventRecord(e1));
@@ -252,6 +281,7 @@ int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
                            : kind == 9 ? (double)sms * 8 * 2 * 18 * 256.0 * iters
                            : kind == 10 ? (double)sms * 16 * 2 * 18 * 256.0 * iters
                            : kind == 11 ? (double)sms * 4 * 2 * 36 * 256.0 * iters
+                           : kind == 12 ? (double)sms * 8 * 4 * 2048.0 * iters
                            : kind == 2 ? (double)grid * (256 * 16.0 + 8 * 4.0 * 256.0) * iters
                                        : (double)sms * 2 * 128 * 144.0 * iters;
   *tflops = 2.0 * fma_count / (best * 1e-3) / 1e12;

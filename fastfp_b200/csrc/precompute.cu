@@ -1,7 +1,7 @@
 // One-time, frequency-independent per-pulsar work for the plain-Fp path:
 //   Sigma = L L^T,  G = L^-1 T^T N^-1  (m x n),  u_r = G r,  w = C^-1 r = N^-1 r - G^T u_r
 // and the packed, tile-contiguous layout the sweep kernel streams with one TMA bulk copy per
-// chunk: packet = [ t[CI] | 1/N[CI] | w[CI] | G in mma-fragment order (g_frag_index) ]  (CI = 16 or 32).
+// chunk: packet = [ (t, 1/N, w, 0)[CI] | G in mma-fragment order (g_frag_index) ]  (CI = 16 or 32).
 //
 // The reference recomputes all of this for every frequency: T^T N^-1 x twice per get_xCy
 // (fastfp/utils.py:51-52) and an LU solve of Sigma per call (utils.py:54), six calls per
@@ -63,15 +63,16 @@ __global__ void build_packets_kernel(double* __restrict__ packets,
   const int CI = pm.ci;
   if (i >= pm.nch * CI) return;
   const int m = pm.m, mp = pm.mpad;
-  const int pkw = CI * (3 + mp);
+  const int pkw = CI * (4 + mp);
   double* pk = packets + pm.pk_off + (size_t)(i / CI) * pkw;
   const int il = i % CI;
   const bool valid = i < pm.n;
   const double ninv = valid ? 1.0 / Nvec[pm.raw_off + i] : 0.0;
-  pk[il] = valid ? toas[pm.raw_off + i] : 0.0;
-  pk[CI + il] = ninv;
-  pk[2 * CI + il] = 0.0;  // w, filled by w_kernel
-  double* gp = pk + 3 * CI;  // G part, fragment order
+  pk[4 * il] = valid ? toas[pm.raw_off + i] : 0.0;
+  pk[4 * il + 1] = ninv;
+  pk[4 * il + 2] = 0.0;  // w, filled by w_kernel
+  pk[4 * il + 3] = 0.0;
+  double* gp = pk + 4 * CI;  // G part, fragment order
   const int nmb = mp >> 3;
   if (!valid) {
     for (int j = 0; j < mp; ++j) gp[g_frag_index(il, j, nmb)] = 0.0;
@@ -101,12 +102,12 @@ __global__ void ur_kernel(const double* __restrict__ packets, const PulsarMeta* 
   const PulsarMeta pm = meta[blockIdx.x];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int CI = pm.ci;
-  const int mp = pm.mpad, pkw = CI * (3 + mp);
+  const int mp = pm.mpad, pkw = CI * (4 + mp);
   const double* pk0 = packets + pm.pk_off;
   for (int j = wid; j < pm.m; j += nw) {
     double acc = 0.0;
     for (int i = lane; i < pm.n; i += 32) {
-      const double g = pk0[(size_t)(i / CI) * pkw + 3 * CI + g_frag_index(i % CI, j, mp >> 3)];
+      const double g = pk0[(size_t)(i / CI) * pkw + 4 * CI + g_frag_index(i % CI, j, mp >> 3)];
       acc = fma(g, res[pm.raw_off + i], acc);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -121,14 +122,14 @@ __global__ void w_kernel(double* __restrict__ packets, const PulsarMeta* __restr
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pm.n) return;
   const int CI = pm.ci;
-  const int mp = pm.mpad, pkw = CI * (3 + mp);
+  const int mp = pm.mpad, pkw = CI * (4 + mp);
   double* pk = packets + pm.pk_off + (size_t)(i / CI) * pkw;
   const int il = i % CI;
-  const double* gp = pk + 3 * CI;
+  const double* gp = pk + 4 * CI;
   const double* u = ur + (size_t)blockIdx.y * MAX_M;
   double acc = 0.0;
   for (int j = 0; j < pm.mfix; ++j) acc = fma(gp[g_frag_index(il, j, mp >> 3)], u[j], acc);
-  pk[2 * CI + il] = res[pm.raw_off + i] * pk[CI + il] - acc;
+  pk[4 * il + 2] = res[pm.raw_off + i] * pk[4 * il + 1] - acc;
 }
 
 int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_res,
