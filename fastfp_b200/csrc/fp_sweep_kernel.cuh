@@ -217,9 +217,8 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
 #pragma unroll
           for (int q = 0; q < 5; ++q) {
             double* a = sl + (size_t)(xx * 5 + q) * NTP;
-            double v = s2[xx][q];
-            if (flushed) v += __ldcg(a);
-            __stcg(a, v);
+            if (flushed) atomicAdd(a, s2[xx][q]);  // result unused -> RED.ADD.F64, no round trip
+            else __stcg(a, s2[xx][q]);
             s2[xx][q] = 0.0;
           }
         flushed = true;
@@ -227,6 +226,7 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
     }
     g += (uint32_t)nch;
     // scalar sums: level-2 totals, then across the 4 lanes that share a frequency
+    if (flushed) __threadfence();
 #pragma unroll
     for (int xx = 0; xx < XW; ++xx)
 #pragma unroll
@@ -361,10 +361,12 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
           for (int q = 0; q < NNB; ++q)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
+              // the slot is private to this thread: first block stores, later blocks add with a
+              // fire-and-forget reduction (RED.ADD.F64) -- a load/add/store chain would expose one L2
+              // round trip per accumulator
               double* a = sl + (size_t)((r * NNB + q) * 2 + e) * NTC;
-              double v = acc[r][q][e];
-              if (flushed) v += __ldcg(a);
-              __stcg(a, v);
+              if (flushed) atomicAdd(a, acc[r][q][e]);
+              else __stcg(a, acc[r][q][e]);
               acc[r][q][e] = 0.0;
             }
         flushed = true;
@@ -374,6 +376,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
 
     // ---- epilogue ------------------------------------------------------------------------
     if (flushed) {
+      __threadfence();  // the reductions above are complete before the read-back
 #pragma unroll
       for (int r = 0; r < NMBW; ++r)
 #pragma unroll
