@@ -24,7 +24,7 @@
 namespace ffp {
 
 constexpr int NB_DT = 8;      // draws per stage-B CTA
-constexpr int NB_LST = 3;     // L^-1 ring depth
+constexpr int NB_LST = 2;     // L^-1 ring depth (two CTAs fit per SM)
 
 __host__ __device__ inline int linv_blocks(int nmbv) {  // blocks (kb, mb >= kb/2) of a lower-tri L^-1
   int n = 0;
@@ -185,69 +185,98 @@ int powerlaw_phiinv_impl(const fastfp_pack* pk, const double* const* Ffreqs, con
 }
 
 // ---- per-(pulsar, draw) factorisation -----------------------------------------------------------
-// S_d = S0 + diag(phiinv_var_d) = L L^T in shared memory; X = L^-1; v = X z'_r. X is written in the
-// A-fragment order of mma.m8n8k4 (lane = (row%8)*4 + k%4), blocks (kb, mb >= kb/2) only.
+// One warp per (pulsar, draw): S_d = S0 + diag(phiinv_var_d) = L L^T in shared memory (right-looking,
+// rows of the trailing update spread over the lanes), X = L^-1 in place (columns from the last to
+// the first; the lower-right part of X is final when column j is formed), v = X z'_r. X is written
+// in the A-fragment order of mma.m8n8k4 (lane = (row%8)*4 + k%4), blocks (kb, mb >= kb/2) only.
+// Only warp-level synchronisation is needed; FW warps (matrices) share a CTA.
 template <int MV>
-__global__ void __launch_bounds__(128) nmfp_factor_kernel(const double* __restrict__ S0,
-                                                          const double* __restrict__ zr,
-                                                          const PulsarMeta* __restrict__ meta,
-                                                          const double* __restrict__ phiinv_var, int64_t ld,
-                                                          double* __restrict__ lf, int lfw) {
-  constexpr int NMBV = MV / 8, LD = MV + 1;
+struct FactorCfg {
+  static constexpr int LD = MV + 1;
+  static constexpr int FW = MV <= 64 ? 4 : 2;                     // matrices per CTA
+  static constexpr size_t SMEM = (size_t)FW * (MV * LD + MV) * 8;
+};
+
+template <int MV>
+__global__ void __launch_bounds__(FactorCfg<MV>::FW * 32) nmfp_factor_kernel(
+    const double* __restrict__ S0, const double* __restrict__ zr, const PulsarMeta* __restrict__ meta,
+    const double* __restrict__ phiinv_var, int64_t ld, double* __restrict__ lf, int lfw, int P, int Db) {
+  constexpr int NMBV = MV / 8, LD = FactorCfg<MV>::LD, FW = FactorCfg<MV>::FW;
   extern __shared__ double sm[];
-  double* A = sm;            // [MV][LD]  S_d -> L
-  double* X = sm + MV * LD;  // [MV][LD]  L^-1
-  const int p = blockIdx.x, d = blockIdx.y, tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int64_t item = (int64_t)blockIdx.x * FW + wrp;
+  if (item >= (int64_t)P * Db) return;  // whole warp leaves together
+  const int d = (int)(item / P), p = (int)(item - (int64_t)d * P);
+  double* A = sm + (size_t)wrp * (MV * LD + MV);  // [MV][LD]
+  double* col = A + MV * LD;                      // [MV] scratch column
   const PulsarMeta pm = meta[p];
   const double* S = S0 + (size_t)p * MV * MV;
   const double* ph = phiinv_var + (size_t)d * ld + pm.var_off;
-  for (int idx = tid; idx < MV * MV; idx += blockDim.x) {
+  for (int idx = lane; idx < MV * MV; idx += 32) {
     const int i = idx / MV, j = idx - i * MV;
-    double v = S[idx];
+    double v = j <= i ? S[idx] : 0.0;
     if (i == j && i < pm.mvar) v += ph[i];
     A[i * LD + j] = v;
-    X[i * LD + j] = 0.0;
   }
-  __syncthreads();
-  for (int j = 0; j < MV; ++j) {  // right-looking Cholesky, lower
-    if (tid == 0) A[j * LD + j] = sqrt(A[j * LD + j]);
-    __syncthreads();
-    const double dj = A[j * LD + j];
-    for (int i = j + 1 + tid; i < MV; i += blockDim.x) A[i * LD + j] = A[i * LD + j] / dj;
-    __syncthreads();
-    const int cnt = MV - j - 1;
-    for (int idx = tid; idx < cnt * cnt; idx += blockDim.x) {
-      const int ii = idx / cnt, kk = idx - ii * cnt;
-      if (kk <= ii) {
-        const int i = j + 1 + ii, k = j + 1 + kk;
-        A[i * LD + k] = fma(-A[i * LD + j], A[k * LD + j], A[i * LD + k]);
+  __syncwarp();
+  // Cholesky, lower, left-looking: column j is a set of dot products of finished rows, so the inner
+  // loops only load (four independent partial sums) and nothing is stored until the column is done
+  for (int j = 0; j < MV; ++j) {
+    double dp = 0.0;  // sum_k L[j][k]^2, lanes share the k range
+    for (int k = lane; k < j; k += 32) dp = fma(A[j * LD + k], A[j * LD + k], dp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, o);
+    const double dj = sqrt(A[j * LD + j] - dp);
+    for (int i = j + 1 + lane; i < MV; i += 32) {
+      const double* ri = A + i * LD;
+      const double* rj = A + j * LD;
+      double a0 = ri[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = 0;
+      for (; k + 3 < j; k += 4) {
+        a0 = fma(-ri[k], rj[k], a0);
+        a1 = fma(-ri[k + 1], rj[k + 1], a1);
+        a2 = fma(-ri[k + 2], rj[k + 2], a2);
+        a3 = fma(-ri[k + 3], rj[k + 3], a3);
       }
+      for (; k < j; ++k) a0 = fma(-ri[k], rj[k], a0);
+      A[i * LD + j] = ((a0 + a1) + (a2 + a3)) / dj;
     }
-    __syncthreads();
+    if (lane == 0) A[j * LD + j] = dj;
+    __syncwarp();
   }
-  // X = L^-1: thread c owns column c (forward substitution of e_c)
-  for (int c = tid; c < MV; c += blockDim.x) {
-    for (int i = c; i < MV; ++i) {
-      double acc = i == c ? 1.0 : 0.0;
-      for (int k = c; k < i; ++k) acc = fma(-A[i * LD + k], X[k * LD + c], acc);
-      X[i * LD + c] = acc / A[i * LD + i];
+  for (int j = MV - 1; j >= 0; --j) {  // X = L^-1 in place
+    const double xjj = 1.0 / A[j * LD + j];
+    for (int i = j + 1 + lane; i < MV; i += 32) col[i] = A[i * LD + j];  // column j of L
+    __syncwarp();
+    for (int i = j + 1 + lane; i < MV; i += 32) {
+      const double* ri = A + i * LD;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // sum_k X[i][k] L[k][j]
+      int k = j + 1;
+      for (; k + 3 <= i; k += 4) {
+        a0 = fma(ri[k], col[k], a0);
+        a1 = fma(ri[k + 1], col[k + 1], a1);
+        a2 = fma(ri[k + 2], col[k + 2], a2);
+        a3 = fma(ri[k + 3], col[k + 3], a3);
+      }
+      for (; k <= i; ++k) a0 = fma(ri[k], col[k], a0);
+      A[i * LD + j] = -((a0 + a1) + (a2 + a3)) * xjj;
     }
+    if (lane == 0) A[j * LD + j] = xjj;
+    __syncwarp();
   }
-  __syncthreads();
-  double* out = lf + ((size_t)d * gridDim.x + p) * lfw;
+  double* out = lf + ((size_t)d * P + p) * lfw;
   const int nblk = linv_blocks(NMBV);
-  for (int idx = tid; idx < nblk * 32; idx += blockDim.x) {
-    const int b = idx >> 5, l = idx & 31;
-    int kb = 0, rem = b;  // invert the block numbering
-    while (rem >= NMBV - kb / 2) { rem -= NMBV - kb / 2; ++kb; }
-    const int mb = kb / 2 + rem;
-    out[idx] = X[(8 * mb + (l >> 2)) * LD + 4 * kb + (l & 3)];
+  int kb = 0, first = 0;  // walk the blocks in (kb, mb) order
+  for (int b = 0; b < nblk; ++b) {
+    if (b - first >= NMBV - kb / 2) { first += NMBV - kb / 2; ++kb; }
+    const int mb = kb / 2 + (b - first);
+    const int row = 8 * mb + (lane >> 2), k = 4 * kb + (lane & 3);
+    out[b * 32 + lane] = k <= row ? A[row * LD + k] : 0.0;
   }
-  // v = X z'_r
   const double* z = zr + (size_t)p * MV;
-  for (int i = tid; i < MV; i += blockDim.x) {
+  for (int i = lane; i < MV; i += 32) {  // v = X z'_r
     double acc = 0.0;
-    for (int k = 0; k <= i; ++k) acc = fma(X[i * LD + k], z[k], acc);
+    for (int k = 0; k <= i; ++k) acc = fma(A[i * LD + k], z[k], acc);
     out[nblk * 32 + i] = acc;
   }
 }
@@ -308,7 +337,6 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
   if (tid == 0) {
     issue_Z(0);
     issue_L(0);
-    if (nit > 1) issue_L(1);
   }
   double fpacc[NB_DT];
 #pragma unroll
@@ -317,7 +345,7 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
   for (int it = 0; it < nit; ++it) {
     const int p = it / nd, dl = it - p * nd;
     if (tid == 0) {
-      if (it + 2 < nit) issue_L(it + 2);                 // stage freed by iteration it-1
+      if (it + 1 < nit) issue_L(it + 1);                 // stage freed by iteration it-1
       if (dl == 0 && p + 1 < ar.P) issue_Z(p + 1);       // buffer freed by pulsar p-1
     }
     if (dl == 0) mbar_wait(&zbar[p & 1], (p >> 1) & 1);
@@ -389,7 +417,7 @@ template <int NMBV>
 static int run_factor_and_stageB(const fastfp_pack* pk, const double* d_phiinv, int64_t ld, int Db,
                                  StageBArgs sb, double* d_lf, cudaStream_t st) {
   constexpr int MV = 8 * NMBV;
-  const size_t fsm = (size_t)2 * MV * (MV + 1) * 8;
+  const size_t fsm = FactorCfg<MV>::SMEM;
   static bool attr_done[64] = {};
   const size_t bsm = (size_t)(2 * MV * 64 + 2 * 160 + NB_LST * sb.lfw) * 8 + 64;
   if (!attr_done[pk->device & 63]) {
@@ -397,8 +425,10 @@ static int run_factor_and_stageB(const fastfp_pack* pk, const double* d_phiinv, 
     FFP_CUDA(cudaFuncSetAttribute(nmfp_stageB_kernel<NMBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     attr_done[pk->device & 63] = true;
   }
-  dim3 gf(pk->P, Db);
-  nmfp_factor_kernel<MV><<<gf, 128, fsm, st>>>(pk->d_S0, pk->d_zr, pk->d_meta, d_phiinv, ld, d_lf, sb.lfw);
+  constexpr int FW = FactorCfg<MV>::FW;
+  const unsigned gf = (unsigned)(((int64_t)pk->P * Db + FW - 1) / FW);
+  nmfp_factor_kernel<MV><<<gf, FW * 32, fsm, st>>>(pk->d_S0, pk->d_zr, pk->d_meta, d_phiinv, ld, d_lf, sb.lfw,
+                                                   pk->P, Db);
   dim3 gb(sb.nt32, (Db + NB_DT - 1) / NB_DT);
   nmfp_stageB_kernel<NMBV><<<gb, 256, bsm, st>>>(sb);
   g_launches += 2;
