@@ -13,7 +13,7 @@ bool sweep_config(int m, KernelCfg* c) {
   if (m <= 40) { *c = {(m + 7) / 8, 4, 1, 16}; return true; }    // 128 frequencies per CTA
   if (m <= 80) { *c = {(m + 7) / 8, 2, 1, 32}; return true; }    // 64 frequencies per CTA
   if (m <= 160) { *c = {(m + 15) / 16, 2, 2, 16}; return true; }  // 32 frequencies per CTA
-  *c = {(m + 31) / 32, 2, 4, 16};                                 // 16 frequencies per CTA
+  *c = {(m + 31) / 32, 2, 4, 16};                                 // 16 frequencies per CTA (m <= 320)
   return true;
 }
 

@@ -74,7 +74,7 @@ def test_get_xcy_general_sigma_uses_pivoted_lu():
 
 
 # every kernel configuration family: m <= 40, <= 80, <= 160, <= 256 (fp_sweep.cu::sweep_config)
-@pytest.mark.parametrize("n_tm,ncomps", [(2, 0), (5, 3), (12, 30), (20, 30), (9, 45), (40, 55), (150, 45)])
+@pytest.mark.parametrize("n_tm,ncomps", [(2, 0), (5, 3), (12, 30), (20, 30), (9, 45), (40, 55), (150, 45), (230, 40)])
 def test_every_kernel_family_against_oracle(n_tm, ncomps):
     m_ = n_tm + 2 * ncomps
     # ragged, not multiples of the chunk size; comfortably more TOAs than basis columns

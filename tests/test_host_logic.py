@@ -96,3 +96,23 @@ def test_synthetic_configs_have_the_survey_shapes():
     assert synth.fp_freqs(200)[0] == 2e-9 and synth.fp_freqs(200)[-1] == 3e-7
     d = synth.draw_samples(small, 5)
     assert d["gw_gamma"].shape == (5,) and len(d) == 2 * 2 + 2
+
+
+def test_compat_package_resolves_reference_import_paths():
+    import importlib
+    import os
+    import sys
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compat")
+    sys.path.insert(0, root)
+    try:
+        for mod, names in (("fastfp.fastfp", ["FastFp"]), ("fastfp.nmfp", ["NMFP", "RN_container", "CURN_container", "GPEcorr_container"]),
+                           ("fastfp.utils", ["get_xCy", "get_mats_fp", "get_mats_nmfp"]), ("fastfp.constants", ["yr", "fyr"])):
+            m = importlib.import_module(mod)
+            for n in names:
+                assert hasattr(m, n)
+        assert importlib.import_module("fastfp.fastfp").FastFp is fastfp_b200.FastFp
+    finally:
+        sys.path.remove(root)
+        for k in [k for k in sys.modules if k == "fastfp" or k.startswith("fastfp.")]:
+            del sys.modules[k]
