@@ -55,6 +55,18 @@ def flops_per_eval(n, m):
     return (4.0 * m + 10.0) * n
 
 
+def measured_traffic(workload):
+    """DRAM bytes of one sweep launch of this workload, from the committed ncu capture
+    (profiles/r1_dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum)."""
+    path = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)[workload]
+        return float(d["dram_bytes_per_launch"]), "profiles/r1_dram_traffic.json (ncu, per launch of one GPU's shard)"
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -288,6 +300,7 @@ def main():
         evals_kernel = float(hi - lo) * wl["P"]
         hbm_peak, peak_src = measured_peaks()
         ach_gbs = evals_kernel * bytes_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(args.workload)
         fp64_peak, _ = _cabi.fp64_peak(1, 20000, device=local)  # DMMA loop, same pipe as DFMA
         ach_tf = evals_kernel * flops_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e12
         line = {
@@ -304,7 +317,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "kernel": "fp_sweep_kernel (persistent, warp-specialised)", "kernel_ms": kern_ms,
                          "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (streaming model); every input is "
                                  "frequency-independent and L2-resident, tiles are reused across 64 frequencies, so "
