@@ -4,11 +4,12 @@ Drop-in for the hot path of gabefreedman/fastfp (``FastFp.calculate_Fp``, ``NMFP
 ``fastfp.utils.get_xCy``): same Python call signatures, with the JAX/XLA kernels replaced by
 hand-written fp64 CUDA kernels for sm_100a behind a C ABI (``include/fastfp_b200.h``).
 """
+from .blockn import BlockNvec
 from .fastfp import FastFp
 from .nmfp import NMFP, CURN_container, GPEcorr_container, RN_container
 from .utils import get_mats_fp, get_mats_nmfp, get_xCy
 from .vmap import vmap
 
 __version__ = "0.1.0"
-__all__ = ["FastFp", "NMFP", "RN_container", "CURN_container", "GPEcorr_container", "get_xCy", "get_mats_fp",
+__all__ = ["BlockNvec", "FastFp", "NMFP", "RN_container", "CURN_container", "GPEcorr_container", "get_xCy", "get_mats_fp",
            "get_mats_nmfp", "vmap"]

@@ -48,6 +48,13 @@ SYMBOLS = {
         [C.c_void_p, c_double_pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
          C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "fastfp_sweep_chunk_toas": (C.c_int, [C.c_int64, C.c_int]),
+    "fastfp_pack_create_blockn": (
+        C.c_int,
+        [C.c_int, C.c_int, c_int64_p, c_int64_p, c_double_pp, c_double_pp, c_double_pp, c_double_pp, c_double_pp,
+         c_double_pp, C.POINTER(C.POINTER(C.c_int32)), c_double_pp, C.POINTER(C.POINTER(C.c_ubyte)), c_int64_p,
+         c_double_pp, C.c_void_p, C.POINTER(C.c_void_p)],
+    ),
     "fastfp_pack_destroy": (None, [C.c_void_p]),
     "fastfp_pack_bytes": (C.c_int64, [C.c_void_p]),
     "fastfp_pack_num_pulsars": (C.c_int, [C.c_void_p]),
@@ -192,6 +199,49 @@ class Pack:
             )
         )
         return cls(h, P, device, True, n, m)
+
+    @classmethod
+    def create_blockn(cls, toas, residuals, Nvecs, Ts, mats, m_fix=None, phiinv_fix=None, device: int = 0,
+                      stream: int = 0) -> "Pack":
+        """Pack with a block-diagonal N (kernel ECORR) for at least one pulsar. ``mats`` are the
+        sigmas (plain Fp, ``m_fix is None``) or the TNTs (nmfp), formed with the block N."""
+        from . import blockn
+
+        P = len(toas)
+        if P < 1 or not (len(residuals) == len(Nvecs) == len(Ts) == len(mats) == P):
+            raise ValueError("toas, residuals, Nvecs, Ts and the matrices must be lists of equal length P >= 1")
+        Ts = [as_f64(T) for T in Ts]
+        mats = [as_f64(a) for a in mats]
+        prep, n, m = [], [], []
+        lib = load()
+        for p in range(P):
+            if Ts[p].ndim != 2 or mats[p].shape != (Ts[p].shape[1],) * 2:
+                raise ValueError(f"pulsar {p}: Ts must be (ntoa, nbasis) and the matrix (nbasis, nbasis)")
+            ci = lib.fastfp_sweep_chunk_toas(Ts[p].shape[1], 1)
+            if ci <= 0:
+                raise ValueError(f"pulsar {p}: basis width {Ts[p].shape[1]} is not supported with a block-diagonal N")
+            d = blockn.prepare(toas[p], residuals[p], Nvecs[p], Ts[p], ci)
+            prep.append(d)
+            n.append(d["toas"].shape[0])
+            m.append(Ts[p].shape[1])
+        require_device()
+        pf = None
+        if m_fix is not None:
+            pf = [as_f64(a).reshape(-1) if len(a) else np.zeros(1) for a in phiinv_fix]
+        i32pp = (C.POINTER(C.c_int32) * P)(*[d["slot_idx"].ctypes.data_as(C.POINTER(C.c_int32)) for d in prep])
+        u8pp = (C.POINTER(C.c_ubyte) * P)(*[d["done_mask"].ctypes.data_as(C.POINTER(C.c_ubyte)) for d in prep])
+        h = C.c_void_p()
+        check(
+            lib.fastfp_pack_create_blockn(
+                device, P, _int64_array(n), _int64_array(m), _ptr_array([d["toas"] for d in prep]),
+                _ptr_array([d["res"] for d in prep]), _ptr_array([d["res_w"] for d in prep]),
+                _ptr_array([d["Nvec"] for d in prep]), _ptr_array([d["T"] for d in prep]), _ptr_array(mats),
+                i32pp, _ptr_array([d["slot_val"] for d in prep]), u8pp,
+                _int64_array(m_fix) if m_fix is not None else None, _ptr_array(pf) if pf is not None else None,
+                C.c_void_p(stream), C.byref(h),
+            )
+        )
+        return cls(h, P, device, m_fix is not None, n, m)
 
     # -- sweeps -------------------------------------------------------------------------
     def fp_sweep(self, freqs, out=None, stream: int = 0, terms: bool = False):

@@ -44,7 +44,7 @@ static int ensure(T** buf, int64_t* cap, int64_t need) {
 // nmfp.cu
 int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res,
                      const double* d_Nvec, const double* d_T, const double* d_TNT,
-                     const double* d_phiinv_fix, cudaStream_t st);
+                     const double* d_phiinv_fix, cudaStream_t st, const BlockNDev* bn = nullptr);
 int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F,
                     const double* d_phiinv_var, int64_t D, double* d_out, cudaStream_t st);
 int powerlaw_phiinv_impl(const fastfp_pack* pk, const double* const* Ffreqs, const double* log10_A,
@@ -61,11 +61,12 @@ struct Staging {
 };
 
 static int pack_layout(fastfp_pack* pk, int P, const int64_t* n, const int64_t* m,
-                       const int64_t* m_fix, const double* const* toas) {
+                       const int64_t* m_fix, const double* const* toas, bool blockn = false) {
   pk->P = P;
   pk->meta.resize(P);
-  int64_t pk_off = 0, L_off = 0, raw_off = 0, T_off = 0;
+  int64_t pk_off = 0, L_off = 0, raw_off = 0, T_off = 0, dm_off = 0;
   int var_off = 0;
+  pk->ecorr = blockn;
   std::map<KernelCfg, std::vector<int>> groups;
   for (int p = 0; p < P; ++p) {
     if (n[p] < 1 || m[p] < 1 || n[p] > 0x7fffff00LL) {
@@ -73,7 +74,9 @@ static int pack_layout(fastfp_pack* pk, int P, const int64_t* n, const int64_t* 
       return FASTFP_ERR_INVALID;
     }
     KernelCfg kc{};
-    if (!sweep_config((int)m[p], &kc)) {
+    // block-diagonal N: one more block of 8 rows (the epoch slots) after the basis rows
+    const int m_rows = blockn ? ((int)m[p] + 7) / 8 * 8 + 8 : (int)m[p];
+    if (m[p] > MAX_M || !sweep_config(m_rows, &kc)) {
       set_error("pulsar " + std::to_string(p) + ": basis width m=" + std::to_string(m[p]) +
                 " exceeds the supported maximum " + std::to_string(MAX_M));
       return FASTFP_ERR_UNSUPPORTED;
@@ -95,6 +98,12 @@ static int pack_layout(fastfp_pack* pk, int P, const int64_t* n, const int64_t* 
       return FASTFP_ERR_INVALID;
     }
     pm.var_off = var_off;
+    pm.dm_off = dm_off;
+    if (blockn && n[p] % kc.ci != 0) {
+      set_error("block-N pack: the TOA count must be a multiple of the chunk size (fastfp_sweep_chunk_toas)");
+      return FASTFP_ERR_INVALID;
+    }
+    dm_off += (n[p] + kc.ci - 1) / kc.ci;
     pm.tabs_max = 0.0;
     if (!toas[p]) { set_error("null toas"); return FASTFP_ERR_INVALID; }
     for (int64_t i = 0; i < n[p]; ++i) {
@@ -156,7 +165,7 @@ static void pack_free(fastfp_pack* pk) {
   DeviceGuard g(pk->device);
   for (auto& gr : pk->groups) cudaFree(gr.d_pidx);
   cudaFree(pk->d_meta); cudaFree(pk->d_packets); cudaFree(pk->d_L); cudaFree(pk->d_info);
-  cudaFree(pk->d_S0); cudaFree(pk->d_zr); cudaFree(pk->d_slab); cudaFree(pk->d_counter);
+  cudaFree(pk->d_S0); cudaFree(pk->d_zr); cudaFree(pk->d_slab); cudaFree(pk->d_counter); cudaFree(pk->d_done_mask);
   cudaFree(pk->d_terms); cudaFree(pk->d_freqs); cudaFree(pk->d_out); cudaFree(pk->d_scratch);
   delete pk;
 }
@@ -240,6 +249,79 @@ int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* 
   if (!rc) rc = nmfp_pack_finish(pk, sg.d_toas, sg.d_res, sg.d_Nvec, sg.d_T, d_TNT, d_pf, st);
   cudaFree(d_TNT);
   cudaFree(d_pf);
+  if (rc) { pack_free(pk); return rc; }
+  *out = pk;
+  return FASTFP_OK;
+}
+
+int fastfp_sweep_chunk_toas(int64_t m, int blockn) {
+  KernelCfg kc{};
+  const int64_t m_rows = blockn ? (m + 7) / 8 * 8 + 8 : m;
+  if (m < 1 || m > MAX_M || !sweep_config((int)m_rows, &kc)) return 0;
+  return kc.ci;
+}
+
+int fastfp_pack_create_blockn(int device, int P, const int64_t* n, const int64_t* m,
+                              const double* const* toas, const double* const* residuals,
+                              const double* const* residuals_w, const double* const* Nvecs,
+                              const double* const* Ts, const double* const* mats,
+                              const int32_t* const* slot_idx, const double* const* slot_val,
+                              const unsigned char* const* done_mask, const int64_t* m_fix,
+                              const double* const* phiinv_fix, void* stream, fastfp_pack_t** out) {
+  if (!out || P < 1 || !n || !m || !toas || !residuals || !residuals_w || !Nvecs || !Ts || !mats ||
+      !slot_idx || !slot_val || !done_mask || (m_fix && !phiinv_fix)) {
+    set_error("fastfp_pack_create_blockn: null argument or P < 1");
+    return FASTFP_ERR_INVALID;
+  }
+  *out = nullptr;
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select CUDA device " + std::to_string(device)); return FASTFP_ERR_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  fastfp_pack* pk = new fastfp_pack();
+  pk->device = device;
+  pk->nmfp = m_fix != nullptr;
+  int rc = pack_layout(pk, P, n, m, m_fix, toas, true);
+  Staging sg;
+  double *d_resw = nullptr, *d_sval = nullptr, *d_mat = nullptr, *d_pf = nullptr;
+  int* d_sidx = nullptr;
+  if (!rc) rc = upload_ragged(&sg.d_toas, toas, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_res, residuals, pk, 0, st);
+  if (!rc) rc = upload_ragged(&d_resw, residuals_w, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_Nvec, Nvecs, pk, 0, st);
+  if (!rc) rc = upload_ragged(&sg.d_T, Ts, pk, 1, st);
+  if (!rc) rc = upload_ragged(&d_sval, slot_val, pk, 0, st);
+  if (!rc) {
+    int64_t ntot = 0, nchtot = 0;
+    for (auto& pm : pk->meta) { ntot += pm.n; nchtot += pm.nch; }
+    cudaError_t e = cudaMalloc(&d_sidx, (size_t)ntot * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&pk->d_done_mask, (size_t)nchtot);
+    for (int p = 0; p < P && e == cudaSuccess; ++p) {
+      const PulsarMeta& pm = pk->meta[p];
+      if (!slot_idx[p] || !done_mask[p]) { rc = FASTFP_ERR_INVALID; set_error("null slot array"); break; }
+      e = cudaMemcpyAsync(d_sidx + pm.raw_off, slot_idx[p], (size_t)pm.n * sizeof(int), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(pk->d_done_mask + pm.dm_off, done_mask[p], (size_t)pm.nch, cudaMemcpyHostToDevice, st);
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "block-N side arrays");
+  }
+  BlockNDev bn{d_resw, d_sidx, d_sval};
+  if (!rc && !pk->nmfp) {
+    rc = upload_ragged(&pk->d_L, mats, pk, 2, st);  // sigmas
+    if (!rc) rc = launch_fp_precompute(pk, sg.d_toas, sg.d_res, sg.d_Nvec, sg.d_T, st, nullptr, &bn);
+  } else if (!rc) {
+    rc = upload_ragged(&d_mat, mats, pk, 2, st);  // TNTs
+    if (!rc) {
+      std::vector<double> pf((size_t)P * MAX_M, 0.0);
+      for (int p = 0; p < P; ++p)
+        for (int j = 0; j < pk->meta[p].mfix; ++j) pf[(size_t)p * MAX_M + j] = phiinv_fix[p][j];
+      cudaError_t e = cudaMalloc(&d_pf, pf.size() * 8);
+      if (e == cudaSuccess) e = cudaMemcpy(d_pf, pf.data(), pf.size() * 8, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) rc = cuda_fail(e, "upload phiinv_fix");
+    }
+    if (!rc) rc = nmfp_pack_finish(pk, sg.d_toas, sg.d_res, sg.d_Nvec, sg.d_T, d_mat, d_pf, st, &bn);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(d_resw); cudaFree(d_sval); cudaFree(d_sidx); cudaFree(d_mat); cudaFree(d_pf);
   if (rc) { pack_free(pk); return rc; }
   *out = pk;
   return FASTFP_OK;

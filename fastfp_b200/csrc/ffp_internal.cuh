@@ -47,7 +47,8 @@ struct SweepCfg {
   static constexpr int KBW = KB / KSPLIT;                 // k-blocks per active producer warp
   static constexpr int NACTIVE = NX >= NWP ? NWP : NX * KSPLIT;  // producer warps with work
   static constexpr int NACC = 2 * NMBW * NNB;  // accumulators per thread
-  static constexpr int SLAB = NACC * NTC + 5 * XW * NTP;  // doubles of level-2 scratch per CTA
+  static constexpr int NACCX = NACC + 3 * NNB;  // + epoch sums of the block-N variant
+  static constexpr int SLAB = NACCX * NTC + 5 * XW * NTP;  // doubles of level-2 scratch per CTA
   static constexpr int FLUSH = FLUSH_TOAS / CI;  // chunks per level-1 block
   // ring depths: sin/cos tiles (producer -> consumer) and G tiles (TMA -> consumer), as deep as
   // the shared-memory budget allows
@@ -79,6 +80,7 @@ struct PulsarMeta {
   int32_t var_off;     // nmfp: offset of this pulsar's varying block in a phiinv_var row
   int32_t ci;          // TOAs per packet for this pulsar's kernel configuration
   double tabs_max;     // max |TOA| (inf if any TOA is not finite): decides the sincos path per tile
+  int64_t dm_off;      // block-N packs: offset of this pulsar's per-chunk slot masks
 };
 
 struct KernelCfg {  // run-time mirror of SweepCfg's parameters
@@ -107,6 +109,8 @@ struct fastfp_pack {
   int P = 0;
   int num_sms = 0;
   bool nmfp = false;
+  bool ecorr = false;            // block-diagonal N (kernel ECORR): 8 epoch-slot rows in the G tiles
+  unsigned char* d_done_mask = nullptr;
   std::vector<ffp::PulsarMeta> meta;
   std::vector<ffp::Group> groups;
   ffp::PulsarMeta* d_meta = nullptr;
@@ -147,9 +151,15 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------
 // precompute.cu
+struct BlockNDev {         // device copies of the block-N (kernel ECORR) side arrays, or all null
+  const double* res_w;     // (N^-1 r) * Nvec per TOA
+  const int* slot_idx;     // epoch slot (0..7) of a TOA inside its chunk, -1 if none
+  const double* slot_val;  // sqrt(beta_e) / Nvec_i
+};
 int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_res,
                          const double* d_Nvec, const double* d_T, cudaStream_t st,
-                         double* d_ur_keep = nullptr);  // d_ur_keep: [P][MAX_M], receives G r
+                         double* d_ur_keep = nullptr,  // [P][MAX_M], receives G r
+                         const BlockNDev* bn = nullptr);
 // fp_sweep*.cu
 struct NmfpOut {      // stage-A outputs of the nmfp path (null for plain Fp)
   double* Z;          // [P][ceil(F/32)][mvpad/4][8][32]  z'_s, z'_c tiles in MMA B-fragment order

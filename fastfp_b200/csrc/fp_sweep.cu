@@ -17,7 +17,7 @@ bool sweep_config(int m, KernelCfg* c) {
   return true;
 }
 
-int sweep_max_slab_doubles() { return 40 * NTC + 10 * NTP; }  // NACC <= 80, XW <= 2 in every configuration
+int sweep_max_slab_doubles() { return (40 + 12) * NTC + 10 * NTP; }  // NACC <= 80, XW <= 2 in every configuration
 
 // out[f] = sum over pulsars in pulsar order, starting from 0 (fastfp.py:71,90).
 __global__ void reduce_terms_kernel(const double* __restrict__ terms, int P, int64_t F,
@@ -43,6 +43,7 @@ int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, dou
   a.Z = nm ? nm->Z : nullptr;
   a.A = nm ? nm->A : nullptr;
   a.mvmax = nm ? nm->mvmax : 0;
+  a.done_mask = pk->d_done_mask;
   a.dbg = dbg;
   for (const Group& g : pk->groups) {
     int rc;

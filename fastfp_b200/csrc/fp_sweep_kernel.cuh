@@ -51,6 +51,7 @@ struct SweepArgs {
   double* Z;              // nmfp: [P][ceil(F/32)][mvmax/4][8][32] (B-fragment order, mvmax = padded)
   double* A;              // nmfp: [P][ceil(F/32)][5][32]
   int mvmax;
+  const unsigned char* done_mask;  // block-N packs: per chunk, which of the 8 epoch slots end there
   int dbg;
 };
 
@@ -101,7 +102,7 @@ struct WorkItem {
 };
 
 // ---- producer role: sin/cos tiles + the five weighted sums -----------------------------------
-template <class C, bool NMFP>
+template <class C, bool NMFP, bool ECORR>
 __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>& sm, volatile int* s_work,
                                               const int pw, const int lane) {
   constexpr int CI = C::CI, XW = C::XW;
@@ -113,7 +114,7 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
   // element (frequency group x, k-block kb) -> S offset (kb*NBT + 2*x + (bf8>>2))*32 + 8*(bf8&3) + 2*bk:
   // the (sin, cos) pair of a (TOA, frequency) is adjacent, so it goes out as one 16-byte store
   const int sofs = (bf8 >> 2) * 32 + 8 * (bf8 & 3) + 2 * bk;
-  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + (size_t)C::NACC * NTC + tidp;
+  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + (size_t)C::NACCX * NTC + tidp;
   uint32_t g = 0;
   for (;;) {
     __syncthreads();  // B1: work item published
@@ -251,7 +252,7 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
 }
 
 // ---- consumer role: the contraction and the epilogue -----------------------------------------
-template <class C, bool NMFP>
+template <class C, bool NMFP, bool ECORR>
 __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>& sm, volatile int* s_work,
                                               const int cw, const int lane) {
   constexpr int NMBW = C::NMBW, NNB = C::NNB;
@@ -289,6 +290,13 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
 #pragma unroll
       for (int q = 0; q < NNB; ++q) acc[r][q][0] = acc[r][q][1] = 0.0;
     bool flushed = false;
+    // block-diagonal N (kernel ECORR): the last row block of the last warp row holds 8 epoch slots;
+    // Y there is sqrt(beta_e) * sum_{i in e} x_i / N_i, folded into these sums when the epoch ends
+    double es[NNB][3];
+#pragma unroll
+    for (int q = 0; q < NNB; ++q) es[q][0] = es[q][1] = es[q][2] = 0.0;
+    const bool slot_warp = ECORR && wm == C::WMW - 1;
+    const unsigned char* dmask = ECORR ? ar.done_mask + pm.dm_off : nullptr;
 
     // fragments of the next k-block -- also across chunk boundaries -- are fetched while the MMAs of
     // the current one run
@@ -353,6 +361,19 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
         mbar_arrive(&sm.g_empty[k % C::GST]);
         mbar_arrive(&sm.s_empty[k % C::SST]);
       }
+      if (ECORR && slot_warp) {
+        // epochs that end in this chunk: e_xy += (sqrt(beta) A_x)(sqrt(beta) A_y); the slot restarts
+        if ((dmask[c] >> (lane >> 2)) & 1) {
+#pragma unroll
+          for (int q = 0; q < NNB; ++q) {
+            const double ys = acc[NMBW - 1][q][0], yc = acc[NMBW - 1][q][1];
+            es[q][0] = fma(ys, ys, es[q][0]);
+            es[q][1] = fma(ys, yc, es[q][1]);
+            es[q][2] = fma(yc, yc, es[q][2]);
+            acc[NMBW - 1][q][0] = acc[NMBW - 1][q][1] = 0.0;
+          }
+        }
+      }
       if ((c + 1) % C::FLUSH == 0 && c + 1 < nch && !(ar.dbg & 4)) {
         // fold the level-1 sums into the level-2 totals of this CTA's scratch slab
 #pragma unroll
@@ -361,6 +382,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
           for (int q = 0; q < NNB; ++q)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
+              if (ECORR && r == NMBW - 1 && slot_warp) continue;  // open epoch sums stay in registers
               // the slot is private to this thread: first block stores, later blocks add with a
               // fire-and-forget reduction (RED.ADD.F64) -- a load/add/store chain would expose one L2
               // round trip per accumulator
@@ -369,6 +391,17 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
               else __stcg(a, acc[r][q][e]);
               acc[r][q][e] = 0.0;
             }
+        if (ECORR && slot_warp) {
+#pragma unroll
+          for (int q = 0; q < NNB; ++q)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+              double* a = sl + (size_t)(C::NACC + q * 3 + e) * NTC;
+              if (flushed) atomicAdd(a, es[q][e]);
+              else __stcg(a, es[q][e]);
+              es[q][e] = 0.0;
+            }
+        }
         flushed = true;
       }
     }
@@ -383,11 +416,17 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
         for (int q = 0; q < NNB; ++q)
 #pragma unroll
           for (int e = 0; e < 2; ++e)
-            acc[r][q][e] += __ldcg(sl + (size_t)((r * NNB + q) * 2 + e) * NTC);
+            if (!(ECORR && r == NMBW - 1 && slot_warp)) acc[r][q][e] += __ldcg(sl + (size_t)((r * NNB + q) * 2 + e) * NTC);
+      if (ECORR && slot_warp) {
+#pragma unroll
+        for (int q = 0; q < NNB; ++q)
+#pragma unroll
+          for (int e = 0; e < 3; ++e) es[q][e] += __ldcg(sl + (size_t)(C::NACC + q * 3 + e) * NTC);
+      }
     }
     // this thread holds Y[row][freq] for rows 8*(wm*NMBW + r) + (lane>>2) and the tile frequencies
     // 4*(wn*NNB + q) + (lane&3): [..][0] is the sin column, [..][1] the cos column
-    const int mfix = NMFP ? pm.mfix : pm.mpad;  // rows below mfix enter the b-sums
+    const int mfix = pm.mfix;  // rows below mfix enter the b-sums (plain Fp: mfix = m)
     double* redB = sm.red;  // [WMW][KF][3]
 #pragma unroll
     for (int q = 0; q < NNB; ++q) {
@@ -396,11 +435,11 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
       for (int r = 0; r < NMBW; ++r) {
         const int j = 8 * (wm * NMBW + r) + (lane >> 2);
         const double ys = acc[r][q][0], yc = acc[r][q][1];
-        if (!NMFP || j < mfix) {
+        if (j < mfix) {
           pss = fma(ys, ys, pss);
           psc = fma(ys, yc, psc);
           pcc = fma(yc, yc, pcc);
-        } else if (j < pm.m) {
+        } else if (NMFP && j < pm.m) {
           // nmfp: rows of the per-draw block go out as z' (canonical 32-frequency tiles)
           const int64_t f = f0 + 4 * (wn * NNB + q) + (lane & 3);
           if (f < ar.F) {
@@ -414,6 +453,11 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
             z[16] = yc;
           }
         }
+      }
+      if (ECORR && slot_warp) {  // the block-N correction enters exactly like the Woodbury b-sums
+        pss += es[q][0];
+        psc += es[q][1];
+        pcc += es[q][2];
       }
       double v3[3] = {pss, psc, pcc};
 #pragma unroll
@@ -467,7 +511,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
   }
 }
 
-template <class C, bool NMFP>
+template <class C, bool NMFP, bool ECORR>
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fp_sweep_kernel(const SweepArgs ar) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SweepSmem<C> sm(smem_raw);
@@ -482,19 +526,19 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fp_sweep_kernel(const S
   __syncthreads();
   if (wid < NWC) {
     reg_alloc<CONSUMER_REGS>();
-    consumer_loop<C, NMFP>(ar, sm, &s_work, wid, lane);
+    consumer_loop<C, NMFP, ECORR>(ar, sm, &s_work, wid, lane);
   } else {
     reg_dealloc<PRODUCER_REGS>();
-    producer_loop<C, NMFP>(ar, sm, &s_work, wid - NWC, lane);
+    producer_loop<C, NMFP, ECORR>(ar, sm, &s_work, wid - NWC, lane);
   }
 }
 
 // ---- launch helpers -------------------------------------------------------------------------
-template <class C, bool NMFP>
+template <class C, bool NMFP, bool ECORR>
 int launch_sweep_cfg(const fastfp_pack* pk, const Group& g, const SweepArgs& base, cudaStream_t st) {
   static bool attr_done[64] = {};
   if (!attr_done[pk->device & 63]) {
-    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_kernel<C, NMFP>,
+    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_kernel<C, NMFP, ECORR>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr_done[pk->device & 63] = true;
   }
@@ -508,7 +552,7 @@ int launch_sweep_cfg(const fastfp_pack* pk, const Group& g, const SweepArgs& bas
   const int64_t resident = (int64_t)CTAS_PER_SM * pk->num_sms;
   const unsigned grid = (unsigned)(nwork < resident ? nwork : resident);
   FFP_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
-  fp_sweep_kernel<C, NMFP><<<grid, NTHREADS, C::SMEM, st>>>(a);
+  fp_sweep_kernel<C, NMFP, ECORR><<<grid, NTHREADS, C::SMEM, st>>>(a);
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
   return 0;
@@ -521,8 +565,12 @@ int dispatch_sweep_w4(const fastfp_pack*, const Group&, const SweepArgs&, bool n
 int dispatch_sweep_wide(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 
 #define FFP_SWEEP_CASE(NMBWv, NNBv, WMWv, CIv)                                                     \
-  if (g.cfg.nmbw == NMBWv && g.cfg.nnb == NNBv && g.cfg.wmw == WMWv && g.cfg.ci == CIv)             \
-    return nmfp ? launch_sweep_cfg<SweepCfg<NMBWv, NNBv, WMWv, CIv>, true>(pk, g, a, st)           \
-                : launch_sweep_cfg<SweepCfg<NMBWv, NNBv, WMWv, CIv>, false>(pk, g, a, st);
+  if (g.cfg.nmbw == NMBWv && g.cfg.nnb == NNBv && g.cfg.wmw == WMWv && g.cfg.ci == CIv) {           \
+    using Cfg_ = SweepCfg<NMBWv, NNBv, WMWv, CIv>;                                                  \
+    if (pk->ecorr) return nmfp ? launch_sweep_cfg<Cfg_, true, true>(pk, g, a, st)                   \
+                               : launch_sweep_cfg<Cfg_, false, true>(pk, g, a, st);                 \
+    return nmfp ? launch_sweep_cfg<Cfg_, true, false>(pk, g, a, st)                                 \
+                : launch_sweep_cfg<Cfg_, false, false>(pk, g, a, st);                               \
+  }
 
 }  // namespace ffp

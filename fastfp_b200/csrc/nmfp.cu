@@ -70,7 +70,8 @@ __global__ void nmfp_extract_kernel(const double* __restrict__ Lbuf, const Pulsa
 }
 
 int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res, const double* d_Nvec,
-                     const double* d_T, const double* d_TNT, const double* d_phiinv_fix, cudaStream_t st) {
+                     const double* d_T, const double* d_TNT, const double* d_phiinv_fix, cudaStream_t st,
+                     const BlockNDev* bn) {
   const int P = pk->P;
   if (pk->mvar_max < 1) { set_error("nmfp pack: every pulsar needs at least one per-draw column (m_fix < m)"); return FASTFP_ERR_INVALID; }
   for (auto& pm : pk->meta)
@@ -82,7 +83,7 @@ int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res,
   g_launches += 1;
   double* d_ur = nullptr;
   FFP_CUDA(cudaMalloc(&d_ur, (size_t)P * MAX_M * sizeof(double)));
-  int rc = launch_fp_precompute(pk, d_toas, d_res, d_Nvec, d_T, st, d_ur);
+  int rc = launch_fp_precompute(pk, d_toas, d_res, d_Nvec, d_T, st, d_ur, bn);
   if (!rc) {
     cudaError_t e = cudaMalloc(&pk->d_S0, (size_t)P * pk->mvpad * pk->mvpad * 8);
     if (e == cudaSuccess) e = cudaMalloc(&pk->d_zr, (size_t)P * pk->mvpad * 8);

@@ -57,7 +57,9 @@ __global__ void build_packets_kernel(double* __restrict__ packets,
                                      const double* __restrict__ Lbuf,
                                      const double* __restrict__ toas,
                                      const double* __restrict__ Nvec,
-                                     const double* __restrict__ T) {
+                                     const double* __restrict__ T,
+                                     const int* __restrict__ slot_idx,
+                                     const double* __restrict__ slot_val) {
   const PulsarMeta pm = meta[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int CI = pm.ci;
@@ -93,6 +95,12 @@ __global__ void build_packets_kernel(double* __restrict__ packets,
     gp[g_frag_index(il, j, nmb)] = g[j];
   }
   for (int j = m; j < mp; ++j) gp[g_frag_index(il, j, nmb)] = 0.0;
+  // block-diagonal N: the last row block holds the epoch slots; this TOA feeds sqrt(beta_e)/N_i
+  // into the slot of its epoch (fp_sweep_kernel folds the slot sums when the epoch ends)
+  if (slot_idx != nullptr) {
+    const int sidx = slot_idx[pm.raw_off + i];
+    if (sidx >= 0) gp[g_frag_index(il, mp - 8 + sidx, nmb)] = slot_val[pm.raw_off + i];
+  }
 }
 
 // u_r[j] = sum_i G[j][i] r_i. One CTA per pulsar, one warp per basis row at a time; lanes
@@ -133,7 +141,8 @@ __global__ void w_kernel(double* __restrict__ packets, const PulsarMeta* __restr
 }
 
 int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_res,
-                         const double* d_Nvec, const double* d_T, cudaStream_t st, double* d_ur_keep) {
+                         const double* d_Nvec, const double* d_T, cudaStream_t st, double* d_ur_keep,
+                         const BlockNDev* bn) {
   const int P = pk->P;
   int nmax = 0;
   for (auto& m : pk->meta) nmax = m.nch * m.ci > nmax ? m.nch * m.ci : nmax;
@@ -141,9 +150,11 @@ int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_
   if (!d_ur) FFP_CUDA(cudaMalloc(&d_ur, (size_t)P * MAX_M * sizeof(double)));
   chol_kernel<<<P, 256, 0, st>>>(pk->d_L, pk->d_meta, pk->d_info);
   dim3 g1((nmax + 127) / 128, P);
-  build_packets_kernel<<<g1, 128, 0, st>>>(pk->d_packets, pk->d_meta, pk->d_L, d_toas, d_Nvec, d_T);
+  build_packets_kernel<<<g1, 128, 0, st>>>(pk->d_packets, pk->d_meta, pk->d_L, d_toas, d_Nvec, d_T,
+                                           bn ? bn->slot_idx : nullptr, bn ? bn->slot_val : nullptr);
   ur_kernel<<<P, 256, 0, st>>>(pk->d_packets, pk->d_meta, d_res, d_ur);
-  w_kernel<<<g1, 128, 0, st>>>(pk->d_packets, pk->d_meta, d_res, d_ur);
+  // with a block-diagonal N the first term of w is N^-1 r, supplied as (N^-1 r) * Nvec
+  w_kernel<<<g1, 128, 0, st>>>(pk->d_packets, pk->d_meta, bn ? bn->res_w : d_res, d_ur);
   g_launches += 4;
   FFP_CUDA(cudaGetLastError());
   FFP_CUDA(cudaStreamSynchronize(st));

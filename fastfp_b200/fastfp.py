@@ -22,6 +22,11 @@ import numpy as np
 from . import _cabi
 
 
+def _plain(a):
+    """array view of an Nvec entry for fingerprinting (block-N objects: their diagonal part)"""
+    return np.asarray(a._nvec if hasattr(a, "_nvec") else a)
+
+
 def _fingerprint(lists) -> tuple:
     """Cheap identity + content key so a pack is rebuilt when the caller passes new data
     (per array: address, shape and a 16-point content sample; no full pass over the data)."""
@@ -29,7 +34,7 @@ def _fingerprint(lists) -> tuple:
     for lst in lists:
         key.append((id(lst), len(lst)))
         for a in lst:
-            a = np.asarray(a)
+            a = _plain(a)
             flat = a.reshape(-1)
             key.append((a.__array_interface__["data"][0], a.shape, flat[:: max(1, flat.size // 16)][:16].tobytes()))
     return tuple(key)
@@ -68,7 +73,12 @@ class FastFp(object):
         if self._pack is None or key != self._pack_key:
             if self._pack is not None:
                 self._pack.close()
-            self._pack = _cabi.Pack.create_fp(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
+            from . import blockn
+
+            if any(blockn.is_block(N) for N in Nvecs):  # block-diagonal N (kernel ECORR)
+                self._pack = _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
+            else:
+                self._pack = _cabi.Pack.create_fp(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
             self._pack_key = key
         return self._pack
 

@@ -240,8 +240,14 @@ class NMFP(object):
                         f"pulsar {p}: basis has {np.shape(T)[1]} columns but the RN_container describes "
                         f"{m_fix[p]} fixed + {sig.Ffreqs.shape[0]} red-noise entries"
                     )
-            self._pack = _cabi.Pack.create_nmfp(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
-                                                [1.0 / f for f in fixed], device=self.device)
+            from . import blockn
+
+            if any(blockn.is_block(N) for N in Nvecs):  # block-diagonal N (kernel ECORR)
+                self._pack = _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
+                                                      [1.0 / f for f in fixed], device=self.device)
+            else:
+                self._pack = _cabi.Pack.create_nmfp(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
+                                                    [1.0 / f for f in fixed], device=self.device)
             self._pack_key = key
         return self._pack
 

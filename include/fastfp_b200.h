@@ -107,6 +107,26 @@ int fastfp_powerlaw_phiinv(const fastfp_pack_t* pack, const double* const* Ffreq
                            const double* curn_Ffreqs, int64_t ncurn, const double* curn_log10_A,
                            const double* curn_gamma, double* phiinv_var_dev, void* stream);
 
+/* ---- block-diagonal N (EcorrKernelNoise) ------------------------------------------------------
+ * The reference leaves this case open ("does not apply ... where N is block-diagonal",
+ * fastfp/utils.py:29-31; README to-do). N = diag(Nvec) + sum_e j_e 1_e 1_e^T over epochs of TOAs.
+ * The host side (fastfp_b200/blockn.py) lays the TOAs out in chunks of fastfp_sweep_chunk_toas(m, 1)
+ * so that every group of 4 TOAs belongs to one epoch, applies the Sherman-Morrison N^-1 to T and r,
+ * and passes per TOA the epoch slot (0..7 inside its chunk, -1 = none) with sqrt(beta_e)/Nvec_i,
+ * beta_e = j_e / (1 + j_e sum_e 1/Nvec), and per chunk the mask of slots whose epoch ends there.
+ *   residuals_w[p] = (N^-1 r) * Nvec,  Ts[p] = (N^-1 T) * Nvec row-wise,  Nvecs[p] = diagonal part
+ *   (inf on padding TOAs);  mats[p] = sigma_p (m_fix == NULL: plain Fp) or TNT_p (nmfp, with m_fix /
+ *   phiinv_fix as in fastfp_nmfp_pack_create), both formed with the block N.
+ * The resulting pack is used with fastfp_fp_sweep / fastfp_nmfp_sweep unchanged. */
+int fastfp_sweep_chunk_toas(int64_t m, int blockn);
+int fastfp_pack_create_blockn(int device, int P, const int64_t* n, const int64_t* m,
+                              const double* const* toas, const double* const* residuals,
+                              const double* const* residuals_w, const double* const* Nvecs,
+                              const double* const* Ts, const double* const* mats,
+                              const int32_t* const* slot_idx, const double* const* slot_val,
+                              const unsigned char* const* done_mask, const int64_t* m_fix,
+                              const double* const* phiinv_fix, void* stream, fastfp_pack_t** out);
+
 void fastfp_pack_destroy(fastfp_pack_t* pack);
 int64_t fastfp_pack_bytes(const fastfp_pack_t* pack);    /* device bytes held */
 int fastfp_pack_num_pulsars(const fastfp_pack_t* pack);
