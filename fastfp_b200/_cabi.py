@@ -65,6 +65,13 @@ SYMBOLS = {
         [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p],
     ),
+    "fastfp_nmfp_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "fastfp_nmfp_stage_ms": (C.c_int, [C.c_void_p, c_double_p]),
+    "fastfp_xcy_blockn": (
+        C.c_int,
+        [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p],
+    ),
     "fastfp_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
 }
 
@@ -312,6 +319,16 @@ class Pack:
             )
         )
 
+    def stage_timing(self, enable: bool = True) -> None:
+        """Bracket the three nmfp stages of later sweeps with CUDA events (measurement aid)."""
+        check(load().fastfp_nmfp_stage_timing(self._h, int(bool(enable))))
+
+    def stage_ms(self):
+        """``(stage A, factor, stage B)`` milliseconds of the last timed nmfp sweep."""
+        out = (C.c_double * 3)()
+        check(load().fastfp_nmfp_stage_ms(self._h, out))
+        return tuple(out)
+
     @property
     def mvar_total(self) -> int:
         return int(load().fastfp_pack_mvar_total(self._h))
@@ -333,6 +350,21 @@ class Pack:
 
 
 def xcy(Nvec, T, sigma, x, y, device: int = 0, stream: int = 0) -> float:
+    from . import blockn
+
+    if blockn.is_block(Nvec):  # block-diagonal N: Sherman-Morrison on the host, same kernel
+        nvec, T, sigma, x, y = as_f64(Nvec._nvec), as_f64(T), as_f64(sigma), as_f64(x), as_f64(y)
+        if T.ndim != 2 or nvec.shape != (T.shape[0],) or x.shape != nvec.shape or y.shape != nvec.shape \
+                or sigma.shape != (T.shape[1],) * 2:
+            raise ValueError("get_xCy: shapes must be Nvec (n,), T (n,m), sigma (m,m), x (n,), y (n,)")
+        B = blockn.BlockNvec(nvec, Nvec._slices, Nvec._jvec)
+        xw, yw = as_f64(B.solve(x) * nvec), as_f64(B.solve(y) * nvec)
+        lib = load()
+        require_device()
+        out = np.empty(1)
+        check(lib.fastfp_xcy_blockn(device, T.shape[0], T.shape[1], _vp(nvec), _vp(T), _vp(sigma), _vp(x), _vp(xw),
+                                    _vp(yw), _vp(out), C.c_void_p(stream)))
+        return float(out[0])
     Nvec, T, sigma, x, y = as_f64(Nvec), as_f64(T), as_f64(sigma), as_f64(x), as_f64(y)
     if T.ndim != 2:
         raise ValueError("get_xCy: T must be 2-D (ntoa, nbasis)")

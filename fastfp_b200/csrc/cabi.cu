@@ -435,6 +435,18 @@ int fastfp_nmfp_sweep(const fastfp_pack_t* pk, const double* freqs, int64_t F,
   return rc;
 }
 
+int fastfp_nmfp_stage_timing(fastfp_pack_t* pk, int enable) {
+  if (!pk || !pk->nmfp) { set_error("fastfp_nmfp_stage_timing: not an nmfp pack"); return FASTFP_ERR_INVALID; }
+  pk->time_stages = enable != 0;
+  return FASTFP_OK;
+}
+
+int fastfp_nmfp_stage_ms(const fastfp_pack_t* pk, double* ms3) {
+  if (!pk || !pk->nmfp || !ms3) { set_error("fastfp_nmfp_stage_ms: not an nmfp pack"); return FASTFP_ERR_INVALID; }
+  for (int i = 0; i < 3; ++i) ms3[i] = pk->stage_ms[i];
+  return FASTFP_OK;
+}
+
 int fastfp_powerlaw_phiinv(const fastfp_pack_t* pk, const double* const* Ffreqs,
                            const double* log10_A, const double* gamma, int64_t D,
                            const double* curn_Ffreqs, int64_t ncurn, const double* curn_log10_A,
@@ -450,8 +462,8 @@ int fastfp_powerlaw_phiinv(const fastfp_pack_t* pk, const double* const* Ffreqs,
                               curn_gamma, phiinv_var_dev, (cudaStream_t)stream);
 }
 
-int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
-               const double* sigma, const double* x, const double* y, double* out, void* stream) {
+static int xcy_run(int device, int64_t n, int64_t m, const double* Nvec, const double* T, const double* sigma,
+                   const double* x, const double* y, const double* x0, double* out, void* stream) {
   if (n < 1 || m < 1 || !Nvec || !T || !sigma || !x || !y || !out) {
     set_error("fastfp_xcy: null argument or non-positive size");
     return FASTFP_ERR_INVALID;
@@ -459,19 +471,20 @@ int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const doubl
   DeviceGuard g(device);
   if (!g.ok) { set_error("cannot select CUDA device " + std::to_string(device)); return FASTFP_ERR_CUDA; }
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t tot = (size_t)(3 * n + n * m + m * m) + (size_t)(m * m + 3 * m + 2);
+  const size_t tot = (size_t)(4 * n + n * m + m * m) + (size_t)(m * m + 3 * m + 2);
   double* d = nullptr;
   FFP_CUDA(cudaMalloc(&d, tot * 8));
-  double *dN = d, *dx = dN + n, *dy = dx + n, *dT = dy + n, *dS = dT + n * m, *dW = dS + m * m;
+  double *dN = d, *dx = dN + n, *dy = dx + n, *dx0 = dy + n, *dT = dx0 + n, *dS = dT + n * m, *dW = dS + m * m;
   double* dO = dW + (m * m + 3 * m);
   cudaError_t e = cudaMemcpyAsync(dN, Nvec, n * 8, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && x0) e = cudaMemcpyAsync(dx0, x0, n * 8, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dT, T, n * m * 8, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dS, sigma, m * m * 8, cudaMemcpyHostToDevice, st);
   int rc = 0;
   if (e != cudaSuccess) rc = cuda_fail(e, "fastfp_xcy upload");
-  if (!rc) rc = launch_xcy(n, m, dN, dT, dS, dx, dy, dW, dO, st);
+  if (!rc) rc = launch_xcy(n, m, dN, dT, dS, dx, dy, x0 ? dx0 : nullptr, dW, dO, st);
   if (!rc) {
     e = cudaMemcpyAsync(out, dO, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -479,6 +492,18 @@ int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const doubl
   }
   cudaFree(d);
   return rc;
+}
+
+int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
+               const double* sigma, const double* x, const double* y, double* out, void* stream) {
+  return xcy_run(device, n, m, Nvec, T, sigma, x, y, nullptr, out, stream);
+}
+
+int fastfp_xcy_blockn(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
+                      const double* sigma, const double* x, const double* xw, const double* yw,
+                      double* out, void* stream) {
+  if (!xw || !yw) { set_error("fastfp_xcy_blockn: null argument"); return FASTFP_ERR_INVALID; }
+  return xcy_run(device, n, m, Nvec, T, sigma, xw, yw, x, out, stream);
 }
 
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms) {

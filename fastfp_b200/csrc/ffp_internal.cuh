@@ -135,6 +135,9 @@ struct fastfp_pack {
   mutable int64_t out_cap = 0;
   mutable double* d_scratch = nullptr;
   mutable int64_t scratch_cap = 0;
+  // optional per-stage timing of nmfp sweeps (fastfp_nmfp_stage_timing): stage A, factor, stage B
+  mutable bool time_stages = false;
+  mutable double stage_ms[3] = {0.0, 0.0, 0.0};
 };
 
 namespace ffp {
@@ -173,7 +176,8 @@ bool sweep_config(int m, KernelCfg* cfg);
 int sweep_max_slab_doubles();
 // xcy.cu
 int launch_xcy(int64_t n, int64_t m, const double* dN, const double* dT, const double* dS,
-               const double* dx, const double* dy, double* d_work, double* d_out, cudaStream_t st);
+               const double* dx, const double* dy, const double* dx0, double* d_work, double* d_out,
+               cudaStream_t st);  // dx0: raw x for the x^T N^-1 y term (null: dx)
 // microbench.cu
 int run_fp64_peak(int kind, int iters, double* tflops, double* ms);
 

@@ -186,99 +186,205 @@ int powerlaw_phiinv_impl(const fastfp_pack* pk, const double* const* Ffreqs, con
 }
 
 // ---- per-(pulsar, draw) factorisation -----------------------------------------------------------
-// One warp per (pulsar, draw): S_d = S0 + diag(phiinv_var_d) = L L^T in shared memory (right-looking,
-// rows of the trailing update spread over the lanes), X = L^-1 in place (columns from the last to
-// the first; the lower-right part of X is final when column j is formed), v = X z'_r. X is written
-// in the A-fragment order of mma.m8n8k4 (lane = (row%8)*4 + k%4), blocks (kb, mb >= kb/2) only.
-// Only warp-level synchronisation is needed; FW warps (matrices) share a CTA.
-template <int MV>
+// One warp per (pulsar, draw): S_d = S0 + diag(phiinv_var_d) = L L^T and X = L^-1 as a BLOCKED
+// algorithm on the fp64 MMA path. The lower triangle lives in shared memory as 8x8 blocks (64 doubles
+// each, columns XOR-swizzled so that the three access patterns below are bank-conflict free):
+//   C layout   lane (R = lane/4, q = lane%4) holds [R][2q], [R][2q+1]   (mma accumulator, one 16-byte access)
+//   A layout   lane holds [R][q], [R][q+4]                                (A operand; also B operand of M^T)
+//   T layout   lane holds [q][R], [q+4][R]                                (B operand of M)
+// Left-looking block Cholesky: block column j = (diagonal block minus the products of finished blocks)
+// -> 8x8 Cholesky AND its triangular inverse in registers (warp shuffles, 8 fused steps) -> the panel
+// below it times inv^T. The diagonal blocks are stored inverted (L_jj itself is never needed again).
+// Then X = L^-1 block row by block row: X_ij = -inv_ii * sum_{k=j..i-1} L_ik X_kj, in place.
+// X leaves in the A-fragment order stage B consumes (blocks (kb, mb >= kb/2)), v = X z'_r is formed by
+// the same fragments on the way out. Only warp-level synchronisation is needed; FW warps share a CTA.
+template <int NMBV>
 struct FactorCfg {
-  static constexpr int LD = MV + 1;
-  static constexpr int FW = MV <= 64 ? 4 : 2;                     // matrices per CTA
-  static constexpr size_t SMEM = (size_t)FW * (MV * LD + MV) * 8;
+  static constexpr int MV = 8 * NMBV;
+  static constexpr int NBLK = NMBV * (NMBV + 1) / 2;
+  static constexpr int WSZ = NBLK * 64 + MV;                       // doubles per warp: blocks + z'_r
+  static constexpr int FW = NMBV <= 4 ? 8 : NMBV <= 8 ? 4 : 2;     // matrices (warps) per CTA
+  static constexpr int CTAS = NMBV <= 4 ? 4 : NMBV <= 8 ? 3 : 2;   // resident CTAs per SM aimed at
+  static constexpr size_t SMEM = (size_t)FW * WSZ * 8;
 };
 
-template <int MV>
-__global__ void __launch_bounds__(FactorCfg<MV>::FW * 32) nmfp_factor_kernel(
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+// 8x8 Cholesky of the (symmetric) block held in C layout and the inverse of its factor, fused: after
+// step j column j of L is final, which is all that row j of X = L^-1 needs. Returns X in C layout with
+// exact zeros above the diagonal.
+__device__ __forceinline__ void chol_inv_8x8(double c0, double c1, double& x0, double& x1, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int R = lane >> 2, q = lane & 3;
+  double y0 = (R == 2 * q) ? 1.0 : 0.0, y1 = (R == 2 * q + 1) ? 1.0 : 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double sel = (j & 1) ? c1 : c0;  // column j lives in the lanes with q == j/2
+    const int qs = j >> 1;
+    const double pj = __shfl_sync(full, sel, j * 4 + qs);
+    const double rinv = 1.0 / sqrt(pj);    // 1 / L[j][j]
+    const double lR = __shfl_sync(full, sel, (lane & ~3) | qs) * rinv;   // L[R][j]
+    const double lc0 = __shfl_sync(full, sel, (8 * q) | qs) * rinv;      // L[2q][j]
+    const double lc1 = __shfl_sync(full, sel, (8 * q + 4) | qs) * rinv;  // L[2q+1][j]
+    if (2 * q > j) c0 = fma(-lR, lc0, c0);
+    if (2 * q + 1 > j) c1 = fma(-lR, lc1, c1);
+    const double xj0 = __shfl_sync(full, y0, j * 4 + q) * rinv;  // row j of X, final
+    const double xj1 = __shfl_sync(full, y1, j * 4 + q) * rinv;
+    if (R > j) {
+      y0 = fma(-lR, xj0, y0);
+      y1 = fma(-lR, xj1, y1);
+    } else if (R == j) {
+      y0 = xj0;
+      y1 = xj1;
+    }
+  }
+  x0 = y0;
+  x1 = y1;
+}
+
+template <int NMBV>
+__global__ void __launch_bounds__(FactorCfg<NMBV>::FW * 32, FactorCfg<NMBV>::CTAS) nmfp_factor_kernel(
     const double* __restrict__ S0, const double* __restrict__ zr, const PulsarMeta* __restrict__ meta,
     const double* __restrict__ phiinv_var, int64_t ld, double* __restrict__ lf, int lfw, int P, int Db) {
-  constexpr int NMBV = MV / 8, LD = FactorCfg<MV>::LD, FW = FactorCfg<MV>::FW;
-  extern __shared__ double sm[];
+  using C = FactorCfg<NMBV>;
+  constexpr int MV = C::MV, FW = C::FW;
+  extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int64_t item = (int64_t)blockIdx.x * FW + wrp;
   if (item >= (int64_t)P * Db) return;  // whole warp leaves together
   const int d = (int)(item / P), p = (int)(item - (int64_t)d * P);
-  double* A = sm + (size_t)wrp * (MV * LD + MV);  // [MV][LD]
-  double* col = A + MV * LD;                      // [MV] scratch column
+  double* W = sm + (size_t)wrp * C::WSZ;
+  double* zs = W + C::NBLK * 64;
+  const int R = lane >> 2, q = lane & 3;
+  const int sw = (R & 2) << 1;
+  const int offC = R * 8 + ((2 * q) ^ sw);           // C layout (16-byte pair)
+  const int offA0 = R * 8 + (q ^ sw), offA1 = offA0 ^ 4;   // A layout
+  const int offT0 = q * 8 + (R ^ ((q & 2) << 1)), offT1 = offT0 + 32;  // T layout
+  auto blk = [&](int i, int j) { return W + (i * (i + 1) / 2 + j) * 64; };
+  auto ld_c = [&](const double* b, double& v0, double& v1) {
+    const double2 t = *reinterpret_cast<const double2*>(b + offC);
+    v0 = t.x; v1 = t.y;
+  };
+  auto st_c = [&](double* b, double v0, double v1) { *reinterpret_cast<double2*>(b + offC) = make_double2(v0, v1); };
+
   const PulsarMeta pm = meta[p];
   const double* S = S0 + (size_t)p * MV * MV;
   const double* ph = phiinv_var + (size_t)d * ld + pm.var_off;
-  for (int idx = lane; idx < MV * MV; idx += 32) {
-    const int i = idx / MV, j = idx - i * MV;
-    double v = j <= i ? S[idx] : 0.0;
-    if (i == j && i < pm.mvar) v += ph[i];
-    A[i * LD + j] = v;
-  }
-  __syncwarp();
-  // Cholesky, lower, left-looking: column j is a set of dot products of finished rows, so the inner
-  // loops only load (four independent partial sums) and nothing is stored until the column is done
-  for (int j = 0; j < MV; ++j) {
-    double dp = 0.0;  // sum_k L[j][k]^2, lanes share the k range
-    for (int k = lane; k < j; k += 32) dp = fma(A[j * LD + k], A[j * LD + k], dp);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, o);
-    const double dj = sqrt(A[j * LD + j] - dp);
-    for (int i = j + 1 + lane; i < MV; i += 32) {
-      const double* ri = A + i * LD;
-      const double* rj = A + j * LD;
-      double a0 = ri[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int k = 0;
-      for (; k + 3 < j; k += 4) {
-        a0 = fma(-ri[k], rj[k], a0);
-        a1 = fma(-ri[k + 1], rj[k + 1], a1);
-        a2 = fma(-ri[k + 2], rj[k + 2], a2);
-        a3 = fma(-ri[k + 3], rj[k + 3], a3);
+  for (int i = 0; i < NMBV; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double2 t = __ldg(reinterpret_cast<const double2*>(S + (size_t)(8 * i + R) * MV + 8 * j + 2 * q));
+      if (i == j && 8 * i + R < pm.mvar) {
+        if (R == 2 * q) t.x += ph[8 * i + R];
+        if (R == 2 * q + 1) t.y += ph[8 * i + R];
       }
-      for (; k < j; ++k) a0 = fma(-ri[k], rj[k], a0);
-      A[i * LD + j] = ((a0 + a1) + (a2 + a3)) / dj;
+      st_c(blk(i, j), t.x, t.y);
     }
-    if (lane == 0) A[j * LD + j] = dj;
+  }
+  for (int i = lane; i < MV; i += 32) zs[i] = zr[(size_t)p * MV + i];
+  __syncwarp();
+
+  // ---- block Cholesky (left-looking), diagonal blocks stored inverted ----
+#pragma unroll
+  for (int j = 0; j < NMBV; ++j) {
+    double bj[NMBV > 1 ? NMBV - 1 : 1][2];  // A layout of the finished blocks of row j
+#pragma unroll
+    for (int k = 0; k < j; ++k) { bj[k][0] = blk(j, k)[offA0]; bj[k][1] = blk(j, k)[offA1]; }
+    double c0, c1, t0 = 0.0, t1 = 0.0;
+    ld_c(blk(j, j), c0, c1);
+#pragma unroll
+    for (int k = 0; k < j; ++k) { dmma884(t0, t1, bj[k][0], bj[k][0]); dmma884(t0, t1, bj[k][1], bj[k][1]); }
+    double x0, x1;
+    chol_inv_8x8(c0 - t0, c1 - t1, x0, x1, lane);
+    st_c(blk(j, j), x0, x1);
+    // panel, part 1: A_ij - sum_k L_ik L_jk^T
+#pragma unroll
+    for (int i = j + 1; i < NMBV; ++i) {
+      double u0 = 0.0, u1 = 0.0, v0, v1;
+#pragma unroll
+      for (int k = 0; k < j; ++k) {
+        dmma884(u0, u1, blk(i, k)[offA0], bj[k][0]);
+        dmma884(u0, u1, blk(i, k)[offA1], bj[k][1]);
+      }
+      ld_c(blk(i, j), v0, v1);
+      st_c(blk(i, j), v0 - u0, v1 - u1);
+    }
+    __syncwarp();
+    // panel, part 2: times inv_jj^T (B operand of M^T = A layout of M)
+    if (j + 1 < NMBV) {
+      const double bi0 = blk(j, j)[offA0], bi1 = blk(j, j)[offA1];
+      double pa[NMBV > 1 ? NMBV - 1 : 1][2];
+#pragma unroll
+      for (int i = j + 1; i < NMBV; ++i) { pa[i - j - 1][0] = blk(i, j)[offA0]; pa[i - j - 1][1] = blk(i, j)[offA1]; }
+      __syncwarp();
+#pragma unroll
+      for (int i = j + 1; i < NMBV; ++i) {
+        double r0 = 0.0, r1 = 0.0;
+        dmma884(r0, r1, pa[i - j - 1][0], bi0);
+        dmma884(r0, r1, pa[i - j - 1][1], bi1);
+        st_c(blk(i, j), r0, r1);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- X = L^-1, block row by block row, in place ----
+#pragma unroll
+  for (int i = 1; i < NMBV; ++i) {
+    double la[NMBV > 1 ? NMBV - 1 : 1][2];
+#pragma unroll
+    for (int k = 0; k < i; ++k) { la[k][0] = blk(i, k)[offA0]; la[k][1] = blk(i, k)[offA1]; }
+    const double nx0 = -blk(i, i)[offA0], nx1 = -blk(i, i)[offA1];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int k = j; k < i; ++k) {
+        dmma884(t0, t1, la[k][0], blk(k, j)[offT0]);
+        dmma884(t0, t1, la[k][1], blk(k, j)[offT1]);
+      }
+      st_c(blk(i, j), t0, t1);
+    }
+    __syncwarp();
+    double tb[NMBV > 1 ? NMBV - 1 : 1][2];
+#pragma unroll
+    for (int j = 0; j < i; ++j) { tb[j][0] = blk(i, j)[offT0]; tb[j][1] = blk(i, j)[offT1]; }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      double r0 = 0.0, r1 = 0.0;
+      dmma884(r0, r1, nx0, tb[j][0]);
+      dmma884(r0, r1, nx1, tb[j][1]);
+      st_c(blk(i, j), r0, r1);
+    }
     __syncwarp();
   }
-  for (int j = MV - 1; j >= 0; --j) {  // X = L^-1 in place
-    const double xjj = 1.0 / A[j * LD + j];
-    for (int i = j + 1 + lane; i < MV; i += 32) col[i] = A[i * LD + j];  // column j of L
-    __syncwarp();
-    for (int i = j + 1 + lane; i < MV; i += 32) {
-      const double* ri = A + i * LD;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // sum_k X[i][k] L[k][j]
-      int k = j + 1;
-      for (; k + 3 <= i; k += 4) {
-        a0 = fma(ri[k], col[k], a0);
-        a1 = fma(ri[k + 1], col[k + 1], a1);
-        a2 = fma(ri[k + 2], col[k + 2], a2);
-        a3 = fma(ri[k + 3], col[k + 3], a3);
-      }
-      for (; k <= i; ++k) a0 = fma(ri[k], col[k], a0);
-      A[i * LD + j] = -((a0 + a1) + (a2 + a3)) * xjj;
-    }
-    if (lane == 0) A[j * LD + j] = xjj;
-    __syncwarp();
-  }
+
+  // ---- out: A-fragment blocks (kb, mb >= kb/2) and v = X z'_r from the same fragments ----
   double* out = lf + ((size_t)d * P + p) * lfw;
-  const int nblk = linv_blocks(NMBV);
-  int kb = 0, first = 0;  // walk the blocks in (kb, mb) order
-  for (int b = 0; b < nblk; ++b) {
-    if (b - first >= NMBV - kb / 2) { first += NMBV - kb / 2; ++kb; }
-    const int mb = kb / 2 + (b - first);
-    const int row = 8 * mb + (lane >> 2), k = 4 * kb + (lane & 3);
-    out[b * 32 + lane] = k <= row ? A[row * LD + k] : 0.0;
+  double acc[NMBV][2];
+#pragma unroll
+  for (int mb = 0; mb < NMBV; ++mb) acc[mb][0] = acc[mb][1] = 0.0;
+  int b = 0;
+#pragma unroll
+  for (int kb = 0; kb < 2 * NMBV; ++kb) {
+    const double zb = zs[4 * kb + q];
+#pragma unroll
+    for (int mb = kb / 2; mb < NMBV; ++mb, ++b) {
+      const double val = blk(mb, kb / 2)[(kb & 1) ? offA1 : offA0];
+      out[b * 32 + lane] = val;
+      dmma884(acc[mb][0], acc[mb][1], val, zb);
+    }
   }
-  const double* z = zr + (size_t)p * MV;
-  for (int i = lane; i < MV; i += 32) {  // v = X z'_r
-    double acc = 0.0;
-    for (int k = 0; k <= i; ++k) acc = fma(A[i * LD + k], z[k], acc);
-    out[nblk * 32 + i] = acc;
+  if (q == 0) {
+#pragma unroll
+    for (int mb = 0; mb < NMBV; ++mb) out[b * 32 + 8 * mb + R] = acc[mb][0];
   }
 }
 
@@ -292,12 +398,6 @@ struct StageBArgs {
   int64_t F, out_ld;
   int P, nt32, Db, lfw;
 };
-
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-      : "+d"(d0), "+d"(d1)
-      : "d"(a), "d"(b));
-}
 
 template <int NMBV>
 __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
@@ -414,24 +514,51 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
   }
 }
 
+// Events between the stages of one sweep (only when the caller asked for stage timing): the interval
+// ending at a mark is charged to that mark's stage (0 = stage A incl. clears, 1 = factor, 2 = stage B).
+struct StageMarks {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, int>> ev;
+  void mark(int stage, cudaStream_t st) {
+    if (!on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ev.push_back({e, stage});
+  }
+  void finish(cudaStream_t st, double* ms3) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    ms3[0] = ms3[1] = ms3[2] = 0.0;
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float t = 0.f;
+      if (ev[i].second >= 0 && cudaEventElapsedTime(&t, ev[i - 1].first, ev[i].first) == cudaSuccess)
+        ms3[ev[i].second] += t;
+    }
+    for (auto& e : ev) cudaEventDestroy(e.first);
+    ev.clear();
+  }
+};
+
 template <int NMBV>
 static int run_factor_and_stageB(const fastfp_pack* pk, const double* d_phiinv, int64_t ld, int Db,
-                                 StageBArgs sb, double* d_lf, cudaStream_t st) {
-  constexpr int MV = 8 * NMBV;
-  const size_t fsm = FactorCfg<MV>::SMEM;
+                                 StageBArgs sb, double* d_lf, cudaStream_t st, StageMarks& marks) {
+  const size_t fsm = FactorCfg<NMBV>::SMEM;
   static bool attr_done[64] = {};
-  const size_t bsm = (size_t)(2 * MV * 64 + 2 * 160 + NB_LST * sb.lfw) * 8 + 64;
+  const size_t bsm = (size_t)(2 * (8 * NMBV) * 64 + 2 * 160 + NB_LST * sb.lfw) * 8 + 64;
   if (!attr_done[pk->device & 63]) {
-    FFP_CUDA(cudaFuncSetAttribute(nmfp_factor_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    FFP_CUDA(cudaFuncSetAttribute(nmfp_factor_kernel<NMBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
     FFP_CUDA(cudaFuncSetAttribute(nmfp_stageB_kernel<NMBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     attr_done[pk->device & 63] = true;
   }
-  constexpr int FW = FactorCfg<MV>::FW;
+  constexpr int FW = FactorCfg<NMBV>::FW;
   const unsigned gf = (unsigned)(((int64_t)pk->P * Db + FW - 1) / FW);
-  nmfp_factor_kernel<MV><<<gf, FW * 32, fsm, st>>>(pk->d_S0, pk->d_zr, pk->d_meta, d_phiinv, ld, d_lf, sb.lfw,
+  nmfp_factor_kernel<NMBV><<<gf, FW * 32, fsm, st>>>(pk->d_S0, pk->d_zr, pk->d_meta, d_phiinv, ld, d_lf, sb.lfw,
                                                    pk->P, Db);
+  marks.mark(1, st);
   dim3 gb(sb.nt32, (Db + NB_DT - 1) / NB_DT);
   nmfp_stageB_kernel<NMBV><<<gb, 256, bsm, st>>>(sb);
+  marks.mark(2, st);
   g_launches += 2;
   FFP_CUDA(cudaGetLastError());
   return 0;
@@ -458,6 +585,9 @@ int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, con
   double* dZ = pk->d_scratch;
   double* dA = dZ + P * nt32_max * (int64_t)MV * 64;
   double* dLf = dA + P * nt32_max * 160;
+  StageMarks marks;
+  marks.on = pk->time_stages;
+  marks.mark(-1, st);
   for (int64_t f0 = 0; f0 < F; f0 += FB) {
     const int64_t Fb = std::min(FB, F - f0);
     const int nt32 = (int)((Fb + 31) / 32);
@@ -466,17 +596,19 @@ int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, con
     FFP_CUDA(cudaMemsetAsync(dA, 0, (size_t)P * nt32 * 160 * 8, st));
     NmfpOut nm{dZ, dA, MV};
     if (int rc = launch_fp_sweep(pk, d_freqs + f0, Fb, nullptr, st, &nm)) return rc;
+    marks.mark(0, st);
     for (int64_t dd = 0; dd < D; dd += DB) {
       const int Db = (int)std::min(DB, D - dd);
       StageBArgs sb{dZ, dA, dLf, d_freqs + f0, d_out + dd * F + f0, Fb, F, P, nt32, Db, lfw};
       const double* ph = d_phiinv_var + dd * pk->mvar_total;
       int rc;
-      if (NMBV == 4) rc = run_factor_and_stageB<4>(pk, ph, pk->mvar_total, Db, sb, dLf, st);
-      else if (NMBV == 8) rc = run_factor_and_stageB<8>(pk, ph, pk->mvar_total, Db, sb, dLf, st);
-      else rc = run_factor_and_stageB<12>(pk, ph, pk->mvar_total, Db, sb, dLf, st);
+      if (NMBV == 4) rc = run_factor_and_stageB<4>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
+      else if (NMBV == 8) rc = run_factor_and_stageB<8>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
+      else rc = run_factor_and_stageB<12>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
       if (rc) return rc;
     }
   }
+  marks.finish(st, pk->stage_ms);
   return 0;
 }
 

@@ -2,6 +2,8 @@
 // operation for operation as the reference writes it (fastfp/utils.py:49-54), including a
 // general LU solve with partial pivoting (what jnp.linalg.solve performs), so it also accepts
 // a Sigma that is not positive definite. One CTA; this is the API-parity op, not the hot path.
+// For a block-diagonal N the caller passes xw = (N^-1 x) * Nvec and yw likewise (Sherman-Morrison
+// on the host): then xw / Nvec = N^-1 x, and x^T N^-1 y = sum x_i * (yw_i / Nvec_i) with the raw x.
 #include "ffp_internal.cuh"
 
 namespace ffp {
@@ -10,7 +12,8 @@ namespace ffp {
 __global__ void xcy_kernel(int64_t n, int m, const double* __restrict__ Nvec,
                            const double* __restrict__ T, const double* __restrict__ sigma,
                            const double* __restrict__ x, const double* __restrict__ y,
-                           double* __restrict__ work, double* __restrict__ out) {
+                           const double* __restrict__ x0, double* __restrict__ work,
+                           double* __restrict__ out) {
   double* LU = work;
   double* TNx = work + (size_t)m * m;
   double* TNy = TNx + m;
@@ -35,7 +38,7 @@ __global__ void xcy_kernel(int64_t n, int m, const double* __restrict__ Nvec,
   }
   // xNy = x . (y / Nvec)
   double a = 0.0;
-  for (int64_t i = tid; i < n; i += blockDim.x) a = fma(x[i], y[i] / Nvec[i], a);
+  for (int64_t i = tid; i < n; i += blockDim.x) a = fma(x0[i], y[i] / Nvec[i], a);
   for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
   if (lane == 0) red[wid] = a;
   for (int idx = tid; idx < m * m; idx += blockDim.x) LU[idx] = sigma[idx];
@@ -94,8 +97,9 @@ __global__ void xcy_kernel(int64_t n, int m, const double* __restrict__ Nvec,
 }
 
 int launch_xcy(int64_t n, int64_t m, const double* dN, const double* dT, const double* dS,
-               const double* dx, const double* dy, double* d_work, double* d_out, cudaStream_t st) {
-  xcy_kernel<<<1, 256, 0, st>>>(n, (int)m, dN, dT, dS, dx, dy, d_work, d_out);
+               const double* dx, const double* dy, const double* dx0, double* d_work, double* d_out,
+               cudaStream_t st) {
+  xcy_kernel<<<1, 256, 0, st>>>(n, (int)m, dN, dT, dS, dx, dy, dx0 ? dx0 : dx, d_work, d_out);
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
   return 0;

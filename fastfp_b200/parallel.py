@@ -50,3 +50,25 @@ def sharded_sweep(local_fn: Callable, freqs, group=None, lead_shape=()):
     nd = len(lead_shape)
     perm = list(range(1, nd + 1)) + [0, nd + 1]
     return recv.permute(*perm).reshape(*lead_shape, world * per)[..., :F]
+
+
+def sharded_draws(local_fn: Callable, D: int, group=None):
+    """Noise-marginalised sweeps shard the DRAW axis instead (every stage of that path -- the
+    per-draw factorisation included -- then splits across ranks; only the small per-frequency
+    stage is repeated). ``local_fn(lo, hi) -> tensor(hi-lo, F)`` runs on every rank for its
+    contiguous draw range; the ``(D, F)`` result is assembled on every rank with one
+    ``all_gather_into_tensor`` (draw-major output, so the gathered buffer needs no re-layout)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return local_fn(0, D)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi, per = shard_bounds(D, rank, world)
+    local = local_fn(lo, hi)
+    F = int(local.shape[-1])
+    send = local if hi - lo == per else torch.cat(
+        [local, torch.zeros(per - (hi - lo), F, dtype=local.dtype, device=local.device)])
+    recv = torch.empty(world * per, F, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.contiguous().view(-1), group=group)
+    return recv[:D]

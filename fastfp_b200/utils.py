@@ -16,10 +16,12 @@ from . import _cabi
 
 
 def get_xCy(Nvec, T, sigma, x, y, device: int = 0):
-    """``x^T C^-1 y`` with ``C = N + T B T^T`` and diagonal ``N`` (reference ``utils.py:49-54``).
+    """``x^T C^-1 y`` with ``C = N + T B T^T`` (reference ``utils.py:49-54``).
 
-    Like the reference this does not apply to a block-diagonal ``N`` (``utils.py:29-31``);
-    a non-vector ``Nvec`` raises ``ValueError``."""
+    ``Nvec`` is the white-noise variance vector, as in the reference; beyond the reference
+    (``utils.py:29-31`` excludes it) a block-diagonal ``N`` is accepted as a
+    :class:`fastfp_b200.BlockNvec` or an enterprise ``ShermanMorrison`` object. Anything else
+    raises ``ValueError``."""
     return np.float64(_cabi.xcy(Nvec, T, sigma, x, y, device=device))
 
 

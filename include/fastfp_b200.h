@@ -132,12 +132,24 @@ int64_t fastfp_pack_bytes(const fastfp_pack_t* pack);    /* device bytes held */
 int fastfp_pack_num_pulsars(const fastfp_pack_t* pack);
 int64_t fastfp_pack_mvar_total(const fastfp_pack_t* pack); /* sum_p m_var[p] (nmfp packs) */
 int64_t fastfp_kernel_launches(void); /* kernels launched by this library so far (process-wide) */
+/* measurement aid: with enable != 0 every later fastfp_nmfp_sweep on this pack brackets its three
+ * stages with CUDA events on the caller's stream and synchronises at the end; fastfp_nmfp_stage_ms
+ * then returns the milliseconds of the last sweep {stage A sweep kernel + clears, per-draw factor
+ * kernel, stage B kernel}. Off by default (no synchronisation on the normal path). */
+int fastfp_nmfp_stage_timing(fastfp_pack_t* pack, int enable);
+int fastfp_nmfp_stage_ms(const fastfp_pack_t* pack, double* ms3);
 
 /* ---- single inner product --------------------------------------------------------------
  * fastfp_xcy: fastfp.utils.get_xCy (fastfp/utils.py:49-54) on the device: host arrays in,
  * x^T C^-1 y out, general (LU, partial pivoting) Sigma solve like jnp.linalg.solve. */
 int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
                const double* sigma, const double* x, const double* y, double* out, void* stream);
+/* the same inner product for a block-diagonal N = diag(Nvec) + epoch blocks: xw = (N^-1 x) * Nvec and
+ * yw = (N^-1 y) * Nvec are prepared on the host (Sherman-Morrison), x is the raw vector; sigma is the
+ * block-N Sigma. (The reference's get_xCy excludes this case, fastfp/utils.py:29-31.) */
+int fastfp_xcy_blockn(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
+                      const double* sigma, const double* x, const double* xw, const double* yw,
+                      double* out, void* stream);
 
 /* ---- measurement helper ----------------------------------------------------------------
  * fastfp_fp64_peak: times a dependent-chain-free DFMA loop (kind 0) or DMMA m8n8k4 loop

@@ -84,3 +84,18 @@ def test_block_n_nmfp_matches_gp_basis_formulation():
         tt, cond = truth.fp_sweep_truth(freqs, pta.toas, pta.residuals, pta.Nvecs, Text, sig_ext)
         tv = tt.sum(0).astype(float)
         assert np.all(np.abs(got[d] - tv) <= 1e-10 * np.abs(tv) + 256 * EPS * cond.sum(0)), d
+
+
+def test_get_xcy_with_block_n():
+    rng = np.random.default_rng(4)
+    n, m = 180, 7
+    T, nvec = rng.standard_normal((n, m)), rng.uniform(0.5, 2.0, n)
+    sl = [slice(0, 5), slice(5, 7), slice(40, 90)]
+    B = BlockNvec(nvec, sl, np.array([0.7, 1.3, 0.2]))
+    phi = rng.uniform(0.1, 3.0, m)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    sigma = T.T @ B.solve(T) + np.diag(1 / phi)
+    C = B.dense() + T @ np.diag(phi) @ T.T  # dense known answer
+    want = x @ np.linalg.solve(C, y)
+    got = fastfp_b200.get_xCy(B, T, sigma, x, y)
+    assert abs(got - want) < 1e-11 * abs(want) + 1e-12

@@ -25,6 +25,10 @@ def _worker(rank, world, port, F, D, out_dir):
     fp = parallel.sharded_sweep(lambda f: f * 3.0 + 1.0, freqs)
     draws = torch.arange(D, dtype=torch.float64)
     nm = parallel.sharded_sweep(lambda f: draws[:, None] * 10.0 + f[None, :] * 1e9, freqs, lead_shape=(D,))
+    Dd = D + 2  # odd draw count: ragged last shard
+    dd = parallel.sharded_draws(
+        lambda lo, hi: torch.arange(lo, hi, dtype=torch.float64)[:, None] * 10.0 + freqs[None, :] * 1e9, Dd)
+    np.save(os.path.join(out_dir, f"dd_{rank}.npy"), dd.numpy())
     np.save(os.path.join(out_dir, f"fp_{rank}.npy"), fp.numpy())
     np.save(os.path.join(out_dir, f"nm_{rank}.npy"), nm.numpy())
     dist.destroy_process_group()
@@ -39,8 +43,11 @@ def test_sharded_sweep_world2(tmp_path, F):
         np.testing.assert_allclose(np.load(tmp_path / f"fp_{r}.npy"), freqs * 3.0 + 1.0, rtol=0, atol=0)
         want = np.arange(D)[:, None] * 10.0 + freqs[None, :] * 1e9
         np.testing.assert_array_equal(np.load(tmp_path / f"nm_{r}.npy"), want)
+        want_d = np.arange(D + 2)[:, None] * 10.0 + freqs[None, :] * 1e9
+        np.testing.assert_array_equal(np.load(tmp_path / f"dd_{r}.npy"), want_d)
 
 
 def test_single_process_is_passthrough():
     f = torch.arange(5, dtype=torch.float64)
     assert torch.equal(parallel.sharded_sweep(lambda x: x + 1, f), f + 1)
+    assert parallel.sharded_draws(lambda lo, hi: torch.zeros(hi - lo, 4), 7).shape == (7, 4)
