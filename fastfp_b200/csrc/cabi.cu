@@ -167,6 +167,8 @@ static void pack_free(fastfp_pack* pk) {
   cudaFree(pk->d_meta); cudaFree(pk->d_packets); cudaFree(pk->d_L); cudaFree(pk->d_info);
   cudaFree(pk->d_S0); cudaFree(pk->d_zr); cudaFree(pk->d_slab); cudaFree(pk->d_counter); cudaFree(pk->d_done_mask);
   cudaFree(pk->d_terms); cudaFree(pk->d_freqs); cudaFree(pk->d_out); cudaFree(pk->d_scratch);
+  cudaFree(pk->d_pl); cudaFreeHost(pk->h_pl);
+  if (pk->pl_event) cudaEventDestroy(pk->pl_event);
   delete pk;
 }
 

@@ -135,6 +135,13 @@ struct fastfp_pack {
   mutable int64_t out_cap = 0;
   mutable double* d_scratch = nullptr;
   mutable int64_t scratch_cap = 0;
+  // staging of the per-draw power-law parameters (fastfp_powerlaw_phiinv): device + pinned host copy,
+  // the event marks the last H2D copy out of h_pl; pl_tab is the frequency table already on the device
+  mutable double* d_pl = nullptr;
+  mutable double* h_pl = nullptr;
+  mutable int64_t pl_cap = 0;
+  mutable cudaEvent_t pl_event = nullptr;
+  mutable std::vector<double> pl_tab;
   // optional per-stage timing of nmfp sweeps (fastfp_nmfp_stage_timing): stage A, factor, stage B
   mutable bool time_stages = false;
   mutable double stage_ms[3] = {0.0, 0.0, 0.0};

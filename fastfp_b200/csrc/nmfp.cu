@@ -139,50 +139,66 @@ static void host_df(const double* Ff, int n, std::vector<double>& df) {
   }
 }
 
+// Host side of RN_container.get_phiinv: no allocation and no synchronisation on the steady path.
+// The per-draw parameters go through a pinned staging buffer owned by the pack (truly asynchronous
+// copies; an event guards its reuse, so the host may run one sweep ahead of the GPU), the
+// frequency tables are uploaded only when they change.
 int powerlaw_phiinv_impl(const fastfp_pack* pk, const double* const* Ffreqs, const double* log10_A,
                          const double* gamma, int64_t D, const double* curn_Ffreqs, int64_t ncurn,
                          const double* curn_log10_A, const double* curn_gamma, double* out, cudaStream_t st) {
   const int P = pk->P;
   const int64_t ld = pk->mvar_total;
-  std::vector<double> hf(ld), hdf(ld), tmp;
+  const size_t nA = (size_t)D * P;
+  const size_t ntab = (size_t)(2 * ld + 2 * ncurn);   // F | df | cF | cdf
+  const size_t npar = 2 * nA + 2 * (size_t)D;          // A | G | cA | cG
+  std::vector<double> tab(ntab), tmp;
   for (int p = 0; p < P; ++p) {
     const PulsarMeta& pm = pk->meta[p];
     if (!Ffreqs[p]) { set_error("fastfp_powerlaw_phiinv: null Ffreqs"); return FASTFP_ERR_INVALID; }
     if (ncurn > pm.mvar) { set_error("fastfp_powerlaw_phiinv: more CURN entries than per-draw columns"); return FASTFP_ERR_INVALID; }
     host_df(Ffreqs[p], pm.mvar, tmp);
-    for (int k = 0; k < pm.mvar; ++k) { hf[pm.var_off + k] = Ffreqs[p][k]; hdf[pm.var_off + k] = tmp[k]; }
+    for (int k = 0; k < pm.mvar; ++k) { tab[pm.var_off + k] = Ffreqs[p][k]; tab[ld + pm.var_off + k] = tmp[k]; }
   }
-  std::vector<double> cdf;
-  if (ncurn > 0) host_df(curn_Ffreqs, (int)ncurn, cdf);
-  const size_t nA = (size_t)D * P;
-  const size_t total = 2 * ld + 2 * nA + 2 * ncurn + 2 * D;
-  double* d = nullptr;
-  FFP_CUDA(cudaMalloc(&d, total * 8));
-  double *dF = d, *dDf = dF + ld, *dA = dDf + ld, *dG = dA + nA, *dcF = dG + nA, *dcdf = dcF + ncurn,
-         *dcA = dcdf + ncurn, *dcG = dcA + D;
-  cudaError_t e = cudaMemcpyAsync(dF, hf.data(), ld * 8, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dDf, hdf.data(), ld * 8, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dA, log10_A, nA * 8, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dG, gamma, nA * 8, cudaMemcpyHostToDevice, st);
   if (ncurn > 0) {
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dcF, curn_Ffreqs, ncurn * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dcdf, cdf.data(), ncurn * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dcA, curn_log10_A, D * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dcG, curn_gamma, D * 8, cudaMemcpyHostToDevice, st);
+    host_df(curn_Ffreqs, (int)ncurn, tmp);
+    for (int64_t k = 0; k < ncurn; ++k) { tab[2 * ld + k] = curn_Ffreqs[k]; tab[2 * ld + ncurn + k] = tmp[k]; }
   }
-  int rc = 0;
-  if (e != cudaSuccess) rc = cuda_fail(e, "fastfp_powerlaw_phiinv upload");
-  if (!rc) {
-    dim3 grid((unsigned)D, P);
-    powerlaw_phiinv_kernel<<<grid, 64, 0, st>>>(pk->d_meta, dF, dDf, dA, dG, P, dcF, dcdf, (int)ncurn, dcA,
-                                                 dcG, out, ld);
-    g_launches += 1;
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host staging vectors go out of scope
-    if (e != cudaSuccess) rc = cuda_fail(e, "powerlaw_phiinv_kernel");
+  if ((int64_t)(ntab + npar) > pk->pl_cap) {
+    if (pk->pl_event) cudaEventSynchronize(pk->pl_event);
+    cudaFree(pk->d_pl); cudaFreeHost(pk->h_pl);
+    pk->d_pl = pk->h_pl = nullptr; pk->pl_cap = 0; pk->pl_tab.clear();
+    FFP_CUDA(cudaMalloc(&pk->d_pl, (ntab + npar) * 8));
+    FFP_CUDA(cudaMallocHost(&pk->h_pl, (ntab + npar) * 8));
+    pk->pl_cap = (int64_t)(ntab + npar);
+    if (!pk->pl_event) FFP_CUDA(cudaEventCreateWithFlags(&pk->pl_event, cudaEventDisableTiming));
+  } else if (pk->pl_event) {
+    FFP_CUDA(cudaEventSynchronize(pk->pl_event));  // the previous call's copies have left the staging buffer
   }
-  cudaFree(d);
-  return rc;
+  double* dT = pk->d_pl;
+  double* dP = dT + ntab;
+  double* hT = pk->h_pl;
+  double* hP = hT + ntab;
+  if (pk->pl_tab != tab) {
+    std::copy(tab.begin(), tab.end(), hT);
+    FFP_CUDA(cudaMemcpyAsync(dT, hT, ntab * 8, cudaMemcpyHostToDevice, st));
+    pk->pl_tab = tab;
+  }
+  std::copy(log10_A, log10_A + nA, hP);
+  std::copy(gamma, gamma + nA, hP + nA);
+  if (ncurn > 0) {
+    std::copy(curn_log10_A, curn_log10_A + D, hP + 2 * nA);
+    std::copy(curn_gamma, curn_gamma + D, hP + 2 * nA + D);
+  }
+  FFP_CUDA(cudaMemcpyAsync(dP, hP, npar * 8, cudaMemcpyHostToDevice, st));
+  FFP_CUDA(cudaEventRecord(pk->pl_event, st));
+  const double *dF = dT, *dDf = dT + ld, *dcF = dT + 2 * ld, *dcdf = dcF + ncurn;
+  const double *dA = dP, *dG = dP + nA, *dcA = dP + 2 * nA, *dcG = dcA + D;
+  dim3 grid((unsigned)D, P);
+  powerlaw_phiinv_kernel<<<grid, 64, 0, st>>>(pk->d_meta, dF, dDf, dA, dG, P, dcF, dcdf, (int)ncurn, dcA, dcG,
+                                               out, ld);
+  g_launches += 1;
+  FFP_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ---- per-(pulsar, draw) factorisation -----------------------------------------------------------
@@ -439,9 +455,13 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
     issue_Z(0);
     issue_L(0);
   }
-  double fpacc[NB_DT];
-#pragma unroll
-  for (int k = 0; k < NB_DT; ++k) fpacc[k] = 0.0;
+  // The 2x2 solves are batched: after the xor-reduction every lane holds the five sums of its frequency
+  // (lane & 3); the lanes with (lane >> 2) == dl keep those of draw dl, and once the NB_DT draws of a
+  // pulsar are through, all 32 lanes solve at once (one (frequency, draw) each) instead of 4 lanes per
+  // iteration -- the fp64 pipe is charged per warp instruction, not per active lane.
+  static_assert(NB_DT == 8, "lane >> 2 indexes the draw inside a CTA");
+  double fpacc = 0.0;
+  double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0, k4 = 0.0;
 
   for (int it = 0; it < nit; ++it) {
     const int p = it / nd, dl = it - p * nd;
@@ -482,10 +502,11 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
       r5[k] += __shfl_xor_sync(0xffffffffu, r5[k], 8);
       r5[k] += __shfl_xor_sync(0xffffffffu, r5[k], 16);
     }
-    if (lane < 4) {
+    if ((lane >> 2) == dl) { k0 = r5[0]; k1 = r5[1]; k2 = r5[2]; k3 = r5[3]; k4 = r5[4]; }
+    if (dl == nd - 1) {  // uniform: the draws of pulsar p are complete
       const double* a = Ab + (p & 1) * 160 + fi;
-      double m00 = a[0] - r5[0], m01 = a[32] - r5[1], m10 = m01, m11 = a[64] - r5[2];
-      const double N0 = a[96] - r5[3], N1 = a[128] - r5[4];
+      double m00 = a[0] - k0, m01 = a[32] - k1, m10 = m01, m11 = a[64] - k2;
+      const double N0 = a[96] - k3, N1 = a[128] - k4;
       double n0 = N0, n1 = N1;
       if (fabs(m10) > fabs(m00)) {  // LU with partial pivoting (jnp.linalg.solve, nmfp.py:117)
         double t0 = m00; m00 = m10; m10 = t0;
@@ -496,21 +517,14 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
       const double u = m11 - lq * m01;
       const double x1 = (n1 - lq * n0) / u;
       const double x0 = (n0 - m01 * x1) / m00;
-      const double term = 0.5 * (N0 * x0 + N1 * x1);
-#pragma unroll
-      for (int k = 0; k < NB_DT; ++k)
-        if (k == dl) fpacc[k] += term;  // pulsar sum in pulsar order, starting from 0 (nmfp.py:98,117)
+      fpacc += 0.5 * (N0 * x0 + N1 * x1);  // pulsar sum in pulsar order, starting from 0 (nmfp.py:98,117)
     }
     __syncthreads();
   }
-  if (lane < 4 && f < ar.F) {
-#pragma unroll
-    for (int k = 0; k < NB_DT; ++k)
-      if (k < nd) {
-        double val = fpacc[k];
-        if (!(fval > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);
-        ar.out[(size_t)(d0 + k) * ar.out_ld + f] = val;
-      }
+  if ((lane >> 2) < nd && f < ar.F) {
+    double val = fpacc;
+    if (!(fval > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);
+    ar.out[(size_t)(d0 + (lane >> 2)) * ar.out_ld + f] = val;
   }
 }
 
