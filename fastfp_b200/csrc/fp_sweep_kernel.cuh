@@ -61,9 +61,6 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
       : "+d"(d0), "+d"(d1)
       : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 template <int R>
 __device__ __forceinline__ void reg_alloc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));

@@ -24,7 +24,6 @@
 namespace ffp {
 
 constexpr int NB_DT = 8;      // draws per stage-B CTA
-constexpr int NB_LST = 2;     // L^-1 ring depth (two CTAs fit per SM)
 
 __host__ __device__ inline int linv_blocks(int nmbv) {  // blocks (kb, mb >= kb/2) of a lower-tri L^-1
   int n = 0;
@@ -415,46 +414,76 @@ struct StageBArgs {
   int P, nt32, Db, lfw;
 };
 
+// One CTA = NH half-tiles of 32 frequencies x NB_DT draws, all pulsars. 8*NH consumer warps (4
+// frequencies each: one n8 MMA column block holds their sin and cos columns) plus one producer warp
+// whose lane 0 drives the TMA rings: the z' tile of a pulsar (double-buffered, reused by the NB_DT draws)
+// and the L^-1 fragments of each (pulsar, draw) (NS stages). Full/empty mbarriers only -- no CTA-wide
+// barrier in the loop, so the warps drift apart by up to NS iterations and the epilogue of one warp
+// (shuffles, the batched 2x2 solves) overlaps the MMAs of the others.
 template <int NMBV>
-__global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
-  constexpr int MV = 8 * NMBV, KBV = 2 * NMBV, ZT = MV * 64;
+struct StageBCfg {
+  static constexpr int MV = 8 * NMBV, ZT = MV * 64;
+  static constexpr int NH = NMBV <= 8 ? 2 : 1;                 // 32-frequency half-tiles per CTA
+  static constexpr int NS = NMBV <= 8 ? 4 : 3;                 // L^-1 ring depth
+  static constexpr int NWB = 8 * NH;                           // consumer warps
+  static constexpr int THREADS = 32 * (NWB + 1);
+  static constexpr int LFW = (NMBV * (NMBV + 1)) * 32 + MV;    // linv_blocks(NMBV) * 32 + MV
+  static constexpr size_t SMEM = (size_t)(2 * NH * ZT + 2 * NH * 160 + NS * LFW) * 8 + (size_t)(4 + 2 * NS) * 8;
+};
+
+template <int NMBV>
+__global__ void __launch_bounds__(StageBCfg<NMBV>::THREADS, 1) nmfp_stageB_kernel(const StageBArgs ar) {
+  using C = StageBCfg<NMBV>;
+  constexpr int KBV = 2 * NMBV, ZT = C::ZT, NH = C::NH, NS = C::NS, NWB = C::NWB, LFW = C::LFW;
   extern __shared__ __align__(128) unsigned char raw[];
-  double* Zb = reinterpret_cast<double*>(raw);       // [2][ZT]
-  double* Ab = Zb + 2 * ZT;                          // [2][160]
-  double* Lb = Ab + 2 * 160;                         // [NB_LST][lfw]
-  uint64_t* zbar = reinterpret_cast<uint64_t*>(Lb + NB_LST * ar.lfw);  // [2]
-  uint64_t* lbar = zbar + 2;                                            // [NB_LST]
+  double* Zb = reinterpret_cast<double*>(raw);       // [2][NH][ZT]
+  double* Ab = Zb + 2 * NH * ZT;                     // [2][NH][160]
+  double* Lb = Ab + 2 * NH * 160;                    // [NS][LFW]
+  uint64_t* zfull = reinterpret_cast<uint64_t*>(Lb + NS * LFW);  // [2]
+  uint64_t* zempty = zfull + 2;                                  // [2]
+  uint64_t* lfull = zempty + 2;                                  // [NS]
+  uint64_t* lempty = lfull + NS;                                 // [NS]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int tile = blockIdx.x, d0 = blockIdx.y * NB_DT;
+  const int t32 = blockIdx.x * NH;                   // first 32-frequency tile of this CTA
+  const int nh = min(NH, ar.nt32 - t32);             // half-tiles that exist (the last CTA may hold one)
+  const int d0 = blockIdx.y * NB_DT;
   const int nd = min(NB_DT, ar.Db - d0);
-  const int bperm = 16 * ((lane >> 2) & 1) + 4 * (lane >> 3) + (lane & 3);
-  const int nblk = linv_blocks(NMBV);
-  const int fi = 4 * w + (lane & 3);                 // this lane group's frequency inside the tile
-  const int64_t f = (int64_t)tile * 32 + fi;
-  const double fval = f < ar.F ? ar.freqs[f] : 1.0;
+  const int nit = ar.P * nd;
   if (tid == 0) {
-    mbar_init(&zbar[0], 1); mbar_init(&zbar[1], 1);
-    for (int s = 0; s < NB_LST; ++s) mbar_init(&lbar[s], 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&zfull[s], 1); mbar_init(&zempty[s], NWB); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&lfull[s], 1); mbar_init(&lempty[s], NWB); }
     fence_barrier_init();
   }
   __syncthreads();
-  auto issue_Z = [&](int p) {
-    uint64_t* b = &zbar[p & 1];
-    mbar_expect_tx(b, (ZT + 160) * 8);
-    tma_load_1d(Zb + (p & 1) * ZT, ar.Z + ((size_t)p * ar.nt32 + tile) * ZT, ZT * 8, b);
-    tma_load_1d(Ab + (p & 1) * 160, ar.A + ((size_t)p * ar.nt32 + tile) * 160, 160 * 8, b);
-  };
-  const int nit = ar.P * nd;
-  auto issue_L = [&](int it) {
-    const int p = it / nd, dl = it - p * nd;
-    uint64_t* b = &lbar[it % NB_LST];
-    mbar_expect_tx(b, ar.lfw * 8);
-    tma_load_1d(Lb + (it % NB_LST) * ar.lfw, ar.lf + ((size_t)(d0 + dl) * ar.P + p) * ar.lfw, ar.lfw * 8, b);
-  };
-  if (tid == 0) {
-    issue_Z(0);
-    issue_L(0);
+
+  if (w == NWB) {  // ---- producer ----
+    if (lane != 0) return;
+    for (int it = 0; it < nit; ++it) {
+      const int p = it / nd, dl = it - p * nd;
+      if (dl == 0) {  // z' tile(s) and the a-terms of pulsar p, before the first L^-1 of that pulsar
+        const int buf = p & 1;
+        if (p >= 2) mbar_wait(&zempty[buf], ((p >> 1) - 1) & 1);
+        mbar_expect_tx(&zfull[buf], (uint32_t)(nh * (ZT + 160) * 8));
+        tma_load_1d(Zb + buf * NH * ZT, ar.Z + ((size_t)p * ar.nt32 + t32) * ZT, (uint32_t)(nh * ZT * 8),
+                    &zfull[buf]);
+        tma_load_1d(Ab + buf * NH * 160, ar.A + ((size_t)p * ar.nt32 + t32) * 160, (uint32_t)(nh * 160 * 8),
+                    &zfull[buf]);
+      }
+      const int s = it % NS;
+      if (it >= NS) mbar_wait(&lempty[s], ((it / NS) - 1) & 1);
+      mbar_expect_tx(&lfull[s], LFW * 8);
+      tma_load_1d(Lb + s * LFW, ar.lf + ((size_t)(d0 + dl) * ar.P + p) * ar.lfw, LFW * 8, &lfull[s]);
+    }
+    return;
   }
+
+  // ---- consumers ----
+  const int h = w >> 3, wl = w & 7;                  // half-tile, warp inside it
+  const int bperm = 16 * ((lane >> 2) & 1) + 4 * (lane >> 3) + (lane & 3);
+  constexpr int nblk = NMBV * (NMBV + 1);
+  const int fi = 4 * wl + (lane & 3);                // this lane group's frequency inside the half-tile
+  const int64_t f = (int64_t)(t32 + h) * 32 + fi;
+  const double fval = f < ar.F ? ar.freqs[f] : 1.0;
   // The 2x2 solves are batched: after the xor-reduction every lane holds the five sums of its frequency
   // (lane & 3); the lanes with (lane >> 2) == dl keep those of draw dl, and once the NB_DT draws of a
   // pulsar are through, all 32 lanes solve at once (one (frequency, draw) each) instead of 4 lanes per
@@ -464,15 +493,11 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
   double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0, k4 = 0.0;
 
   for (int it = 0; it < nit; ++it) {
-    const int p = it / nd, dl = it - p * nd;
-    if (tid == 0) {
-      if (it + 1 < nit) issue_L(it + 1);                 // stage freed by iteration it-1
-      if (dl == 0 && p + 1 < ar.P) issue_Z(p + 1);       // buffer freed by pulsar p-1
-    }
-    if (dl == 0) mbar_wait(&zbar[p & 1], (p >> 1) & 1);
-    mbar_wait(&lbar[it % NB_LST], (it / NB_LST) & 1);
-    const double* zt = Zb + (p & 1) * ZT + w * 32 + bperm;
-    const double* lt = Lb + (it % NB_LST) * ar.lfw;
+    const int p = it / nd, dl = it - p * nd, buf = p & 1, s = it % NS;
+    if (dl == 0) mbar_wait(&zfull[buf], (p >> 1) & 1);
+    mbar_wait(&lfull[s], (it / NS) & 1);
+    const double* zt = Zb + (buf * NH + h) * ZT + wl * 32 + bperm;
+    const double* lt = Lb + s * LFW;
     double acc[NMBV][2];
 #pragma unroll
     for (int mb = 0; mb < NMBV; ++mb) acc[mb][0] = acc[mb][1] = 0.0;
@@ -496,6 +521,8 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
       r5[3] = fma(us, vv, r5[3]);
       r5[4] = fma(uc, vv, r5[4]);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&lempty[s]);  // this warp is done with the L^-1 stage
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       r5[k] += __shfl_xor_sync(0xffffffffu, r5[k], 4);
@@ -504,9 +531,11 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
     }
     if ((lane >> 2) == dl) { k0 = r5[0]; k1 = r5[1]; k2 = r5[2]; k3 = r5[3]; k4 = r5[4]; }
     if (dl == nd - 1) {  // uniform: the draws of pulsar p are complete
-      const double* a = Ab + (p & 1) * 160 + fi;
+      const double* a = Ab + (buf * NH + h) * 160 + fi;
       double m00 = a[0] - k0, m01 = a[32] - k1, m10 = m01, m11 = a[64] - k2;
       const double N0 = a[96] - k3, N1 = a[128] - k4;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&zempty[buf]);  // z' tile and a-terms of pulsar p are consumed
       double n0 = N0, n1 = N1;
       if (fabs(m10) > fabs(m00)) {  // LU with partial pivoting (jnp.linalg.solve, nmfp.py:117)
         double t0 = m00; m00 = m10; m10 = t0;
@@ -519,7 +548,6 @@ __global__ void __launch_bounds__(256) nmfp_stageB_kernel(const StageBArgs ar) {
       const double x0 = (n0 - m01 * x1) / m00;
       fpacc += 0.5 * (N0 * x0 + N1 * x1);  // pulsar sum in pulsar order, starting from 0 (nmfp.py:98,117)
     }
-    __syncthreads();
   }
   if ((lane >> 2) < nd && f < ar.F) {
     double val = fpacc;
@@ -559,7 +587,8 @@ static int run_factor_and_stageB(const fastfp_pack* pk, const double* d_phiinv, 
                                  StageBArgs sb, double* d_lf, cudaStream_t st, StageMarks& marks) {
   const size_t fsm = FactorCfg<NMBV>::SMEM;
   static bool attr_done[64] = {};
-  const size_t bsm = (size_t)(2 * (8 * NMBV) * 64 + 2 * 160 + NB_LST * sb.lfw) * 8 + 64;
+  const size_t bsm = StageBCfg<NMBV>::SMEM;
+  if (sb.lfw != StageBCfg<NMBV>::LFW) { set_error("internal: L^-1 fragment width mismatch"); return FASTFP_ERR_UNSUPPORTED; }
   if (!attr_done[pk->device & 63]) {
     FFP_CUDA(cudaFuncSetAttribute(nmfp_factor_kernel<NMBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
     FFP_CUDA(cudaFuncSetAttribute(nmfp_stageB_kernel<NMBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
@@ -570,8 +599,8 @@ static int run_factor_and_stageB(const fastfp_pack* pk, const double* d_phiinv, 
   nmfp_factor_kernel<NMBV><<<gf, FW * 32, fsm, st>>>(pk->d_S0, pk->d_zr, pk->d_meta, d_phiinv, ld, d_lf, sb.lfw,
                                                    pk->P, Db);
   marks.mark(1, st);
-  dim3 gb(sb.nt32, (Db + NB_DT - 1) / NB_DT);
-  nmfp_stageB_kernel<NMBV><<<gb, 256, bsm, st>>>(sb);
+  dim3 gb((sb.nt32 + StageBCfg<NMBV>::NH - 1) / StageBCfg<NMBV>::NH, (Db + NB_DT - 1) / NB_DT);
+  nmfp_stageB_kernel<NMBV><<<gb, StageBCfg<NMBV>::THREADS, bsm, st>>>(sb);
   marks.mark(2, st);
   g_launches += 2;
   FFP_CUDA(cudaGetLastError());
