@@ -341,6 +341,7 @@ def run_nmfp(args, wl, rank, world, local):
         ach_b = evals_rank * fl_b / (stage[2] * 1e-3) / 1e12
         ach_all = evals_rank * fl_total / (stage.sum() * 1e-3) / 1e12
         ach_gbs = evals_rank * bytes_per_eval(wl["n"], M_BASIS) / (stage.sum() * 1e-3) / 1e9
+        nmfp_traffic = 1.596071e9 + 12.80512e6 if (F, hi - lo) == (1000, 1000) else None  # ncu, C3 shapes only
         line = {
             "metric": "Fp evals/sec (freqs x pulsars x draws)", "value": evals_step / ms_step * 1e3,
             "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -358,21 +359,25 @@ def run_nmfp(args, wl, rank, world, local):
                     "d2h_bytes_per_step": int(8 * F * D_total * world)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "all three nmfp stages", "kernel_ms": float(stage.sum()),
-                         "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference re-streams every input "
-                                 "for each (frequency, draw)); here they are read once per frequency (stage A) and "
-                                 "the per-draw work runs on mv x mv blocks, so this effective figure exceeds 1 by "
-                                 "construction -- the binding roofline is roofline_fp64"},
-            "roofline_fp64": {"bound": "fp64 pipe (DFMA/DMMA share it)", "kernel": "nmfp_stageB_kernel",
-                              "achieved": ach_b, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_b / fp64_peak,
-                              "kernel_ms": float(stage[2]), "flops_per_eval": fl_b,
-                              "all_stages": {"achieved": ach_all, "frac": ach_all / fp64_peak,
-                                             "flops_per_eval": fl_total, "ms": float(stage.sum())},
-                              "stage_ms": {"stage_A_sweep": float(stage[0]), "factor": float(stage[1]),
-                                           "stage_B": float(stage[2])},
-                              "peak_source": "measured on this GPU: fastfp_fp64_peak (mma.m8n8k4.f64 loop)"},
+            "roofline": {"bound": "tensor", "pipe": "fp64 tensor path (DMMA; DFMA shares the pipe)",
+                         "kernel": "nmfp_stageB_kernel", "achieved": ach_b, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach_b / fp64_peak, "kernel_ms": float(stage[2]), "flops_per_eval": fl_b,
+                         "traffic": nmfp_traffic,
+                         "traffic_source": "profiles/r1_nmfp_ncu_summary.md (ncu dram__bytes_read+write, one launch)",
+                         "all_stages": {"achieved": ach_all, "frac": ach_all / fp64_peak,
+                                        "flops_per_eval": fl_total, "ms": float(stage.sum())},
+                         "stage_ms": {"stage_A_sweep": float(stage[0]), "factor": float(stage[1]),
+                                      "stage_B": float(stage[2])},
+                         "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
+                                        "MEASURED_PEAKS.json holds no fp64 figure",
+                         "note": "algorithmic flops 2 mv^2 + 10 mv per eval for stage B (exact triangle, mv = 60); the "
+                                 "kernel executes 72 8x4 blocks per 4 frequencies against 57 for the exact triangle"},
+            "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
+                             "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference re-streams every input "
+                                     "for each (frequency, draw)); here they are read once per frequency (stage A) "
+                                     "and the per-draw work runs on mv x mv blocks, so this effective figure exceeds "
+                                     "1 by construction -- HBM is not the bound"},
         }
         if not args.no_cpu_baseline and world == 1:
             rate, meta = cpu_reference_rate_nmfp(wl, steps=1)
@@ -547,18 +552,23 @@ def main():
                     "h2d_bytes_per_step": int(8 * F_total), "d2h_bytes_per_step": int(8 * F_total * world)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": peak_src,
+            # The binding roofline: the contraction runs on the fp64 tensor path (DMMA), which shares one
+            # pipe with DFMA; peak = the same pipe measured on this GPU with a pure mma.m8n8k4.f64 loop.
+            "roofline": {"bound": "tensor", "pipe": "fp64 tensor path (DMMA; DFMA shares the pipe)",
+                         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
+                                        "MEASURED_PEAKS.json holds no fp64 figure",
                          "kernel": "fp_sweep_kernel (persistent, warp-specialised)", "kernel_ms": kern_ms,
-                         "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (streaming model); every input is "
-                                 "frequency-independent and L2-resident, tiles are reused across 64 frequencies, so "
-                                 "this effective-bandwidth figure legitimately exceeds 1 -- the binding roofline is "
-                                 "roofline_fp64"},
-            "roofline_fp64": {"bound": "fp64 pipe (DFMA/DMMA share it)", "achieved": ach_tf, "peak": fp64_peak,
-                              "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                              "peak_source": "measured on this GPU: fastfp_fp64_peak (mma.m8n8k4.f64 loop)",
-                              "flops_per_eval": flops_per_eval(wl["n"], M_BASIS)},
+                         "flops_per_eval": flops_per_eval(wl["n"], M_BASIS),
+                         "note": "algorithmic flops (4m+10)n per eval: Y = G[s c] and the five weighted sums; the "
+                                 "sincos generation that must also run on this pipe is not counted"},
+            "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                             "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference's streaming model); "
+                                     "every input is frequency-independent and L2-resident and tiles are reused "
+                                     "across 64 frequencies, so this effective figure exceeds 1 by construction -- "
+                                     "HBM is not the bound, measured DRAM traffic per launch is `traffic`"},
         }
         if not args.no_cpu_baseline and world == 1:
             rate, meta = cpu_reference_rate(wl, steps=1)
