@@ -21,7 +21,10 @@
  *    the pack's device; `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *    Calls taking a stream are asynchronous on it unless they copy to host memory, in which
  *    case they synchronise the stream before returning;
- *  - the caller owns every input and output buffer; a pack owns only its own device memory.
+ *  - the caller owns every input and output buffer; a pack owns only its own device memory;
+ *  - threads: different packs may be used from different host threads concurrently; one pack
+ *    carries scratch buffers and a work counter, so calls on the SAME pack must be serialised
+ *    by the caller (issuing them on one stream from one thread at a time is enough).
  */
 #ifndef FASTFP_B200_H
 #define FASTFP_B200_H

@@ -148,3 +148,31 @@ def test_nmfp_consistent_with_plain_fp():
     well = freqs > 40 / pta.Tspan
     assert np.abs(nm[well] / fp[well] - 1).max() < 1e-9
     assert np.abs(nm / fp - 1).max() < 1e-5
+
+
+def test_nmfp_full_size_properties():
+    """BASELINE configs[2] shapes (45 pulsars x 5000 TOAs, m = 72): properties that do not need the oracle
+    at every bin -- draw batching and draw order do not change a value, a draw equal to the fixed noise
+    values reproduces the plain-Fp path (same Sigma), r -> 2r scales exactly by 4."""
+    pta = synth.make_config("C3")
+    curn = CURN_container(pta.Ffreqs)
+    sigs = [RN_container(q, Ffreqs=pta.Ffreqs, add_curn=True, curn_container=curn) for q in pta.psrs]
+    nm = NMFP(pta.psrs, sigs)
+    mats = (pta.Nvecs, pta.Ts, pta.TNTs)
+    D, F = 19, 150  # ragged: not multiples of the 8-draw / 64-frequency CTA tiles
+    samples = synth.draw_samples(pta, D)
+    freqs = synth.fp_freqs(10_000)[:: 10_000 // F][:F]
+    full = nm(freqs, samples, *mats)
+    assert full.shape == (D, F) and np.all(np.isfinite(full)) and full.min() > 0
+    perm = np.random.default_rng(0).permutation(D)
+    np.testing.assert_array_equal(nm(freqs, {k: v[perm] for k, v in samples.items()}, *mats), full[perm])
+    np.testing.assert_array_equal(nm(freqs, {k: v[5:9] for k, v in samples.items()}, *mats), full[5:9])
+    np.testing.assert_array_equal(nm(freqs[37:101], samples, *mats), full[:, 37:101])
+    psr2 = [Psr(q.toas, 2.0 * q.residuals) for q in pta.psrs]
+    np.testing.assert_array_equal(NMFP(psr2, sigs)(freqs, samples, *mats), 4.0 * full)
+    # plain-Fp path with the Sigma of draw 3, built on the host the way NMFP._get_sigmas does
+    pars = {k: v[3] for k, v in samples.items()}
+    fp = fastfp_b200.FastFp(pta.psrs)(freqs, pta.Nvecs, pta.Ts, nm._get_sigmas(pars, pta.TNTs))
+    well = freqs > 40 / pta.Tspan
+    assert np.abs(full[3][well] / fp[well] - 1).max() < 1e-9
+    assert np.abs(full[3] / fp - 1).max() < 1e-5
