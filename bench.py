@@ -240,7 +240,7 @@ def run_reference_nmfp(args, wl, rank, world):
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_nmfp(args, wl, rank, world, local):
@@ -257,6 +257,7 @@ def run_nmfp(args, wl, rank, world, local):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -306,9 +307,10 @@ def run_nmfp(args, wl, rank, world, local):
         return float(t.item())
 
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 1.5:
-        step_device()
+    while time.perf_counter() - t_spin < 1.5:  # rank-local spin-up (no collective: wall-clock bounded)
+        nm(freqs_dev, mine, *mats)
         torch.cuda.synchronize()
+    barrier()
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
@@ -383,7 +385,7 @@ def run_nmfp(args, wl, rank, world, local):
             rate, meta = cpu_reference_rate_nmfp(wl, steps=1)
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": meta["cores"], "kind": meta["kind"],
                                     "sample": meta["sample"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -403,7 +405,7 @@ def run_reference(args, wl, rank, world):
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(key, wl, gpus):
@@ -415,7 +417,21 @@ def workload_name(key, wl, gpus):
             f"{wl['F_per_gpu']} frequencies per GPU x {gpus} GPU(s), red+white Woodbury C, fp64")
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else that libraries write to
+    fd 1 (NCCL prints its version banner there) was redirected to stderr in main()."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -448,6 +464,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -499,11 +516,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # clock spin-up (the SM clock needs ~0.4 s of load to leave its idle state), then W warm-ups
+    # clock spin-up (the SM clock needs ~0.4 s of load to leave its idle state), then W warm-ups. The
+    # spin-up is wall-clock bounded, so it must stay rank-local: no collective inside (ranks would run
+    # different numbers of them and deadlock).
+    shard0 = freqs_dev[lo:hi].contiguous()
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 1.5:
-        step_device()
+        fp.calculate_Fp(shard0, *mats)
         torch.cuda.synchronize()
+    barrier()
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
@@ -574,7 +595,7 @@ def main():
             rate, meta = cpu_reference_rate(wl, steps=1)
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": meta["cores"], "kind": meta["kind"],
                                     "sample": meta["sample"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
