@@ -16,14 +16,15 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fastfp_b200 import NMFP, CURN_container, RN_container, get_mats_nmfp, vmap  # noqa: E402
+from fastfp_b200 import NMFP, CURN_container, RN_container, chains, get_mats_nmfp, vmap  # noqa: E402
 
 
 def create_freqarray(Tspan, ncomps=30):
     return np.repeat(1.0 * np.arange(1, ncomps + 1) / Tspan, 2)
 
 
-def main(synthetic, savefile="nmfp_out", inc_cp=True, nrncomps=30, ngwbcomps=30, ncwfreqs=100, nsamples=1000):
+def main(synthetic, savefile="nmfp_out", inc_cp=True, nrncomps=30, ngwbcomps=30, ncwfreqs=100, nsamples=1000,
+         chainfile=None, batch_size=None):
     logging.basicConfig(format="%(levelname)s: %(message)s", level=logging.INFO)
     logger = logging.getLogger(__name__)
     from fastfp_b200 import synth
@@ -43,12 +44,23 @@ def main(synthetic, savefile="nmfp_out", inc_cp=True, nrncomps=30, ngwbcomps=30,
     logger.info(f"Precompute matrix wall time: {time.perf_counter() - t_start:.2f} s")
 
     freqs = np.arange(1, ncwfreqs + 1) / Tspan
-    samples = synth.draw_samples(pta, nsamples)  # dict name -> (nsamples,), what map_params builds
+    # parameter order of the chain columns = pta.params order in the reference (run_nmfp.py:174-186)
+    param_names = [f"{psr.name}_red_noise_{k}" for psr in psrs for k in ("gamma", "log10_A")] + \
+                  (["gw_gamma", "gw_log10_A"] if inc_cp else [])
+    if chainfile is None:  # stand-in MCMC chain, written in the PTMCMC text layout and read back
+        os.makedirs("res", exist_ok=True)
+        chainfile = f"res/{savefile}_chain_1.txt"
+        chains.write_chain(chainfile, synth.draw_samples(pta, 2 * nsamples), param_names)
+    samples, _ = chains.draws_from_chain(chainfile, param_names, nsamples)  # 25% burn-in, distinct rows
 
     t_start = time.perf_counter()
     vmap_f = vmap(nmfp, in_axes=(0, None, None, None, None))
     vmap_g = vmap(vmap_f, in_axes=(None, 0, None, None, None))
-    nmfp_vals = np.asarray(vmap_g(freqs, samples, Nvecs, Ts, TNTs))
+    if batch_size:  # the reference's draw batches (run_nmfp.py:256-270); only bounds the host-side output here
+        nmfp_vals = np.vstack([np.asarray(vmap_g(freqs, part, Nvecs, Ts, TNTs))
+                               for part in chains.draw_batches(samples, batch_size)])
+    else:
+        nmfp_vals = np.asarray(vmap_g(freqs, samples, Nvecs, Ts, TNTs))
     logger.info(f"Noise marginalized Fp-statistic wall time: {time.perf_counter() - t_start:.2f} s")
 
     os.makedirs("res", exist_ok=True)
@@ -65,4 +77,6 @@ if __name__ == "__main__":
     parser.add_argument("--ngwbcomps", type=int, default=30)
     parser.add_argument("--ncwfreqs", type=int, default=100)
     parser.add_argument("--nsamples", type=int, default=1000)
+    parser.add_argument("--chainfile", type=str, default=None, help="PTMCMC text chain (last 4 columns = sampler metadata)")
+    parser.add_argument("--batch_size", type=int, default=None)
     main(**vars(parser.parse_args()))

@@ -65,6 +65,10 @@ SYMBOLS = {
         [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p],
     ),
+    "fastfp_tnt": (
+        C.c_int,
+        [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "fastfp_nmfp_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "fastfp_nmfp_stage_ms": (C.c_int, [C.c_void_p, c_double_p]),
     "fastfp_xcy_blockn": (
@@ -347,6 +351,24 @@ class Pack:
             self.close()
         except Exception:
             pass
+
+
+def tnt(Nvec, T, phiinv=None, device: int = 0, stream: int = 0) -> np.ndarray:
+    """``T^T N^-1 T`` (``+ diag(phiinv)``) on the device; diagonal ``N`` given as the variance vector."""
+    Nvec, T = as_f64(Nvec), as_f64(T)
+    if T.ndim != 2 or Nvec.shape != (T.shape[0],):
+        raise ValueError("tnt: shapes must be Nvec (n,), T (n, m)")
+    ph = None
+    if phiinv is not None:
+        ph = as_f64(phiinv)
+        if ph.shape != (T.shape[1],):
+            raise ValueError("tnt: phiinv must have shape (m,)")
+    lib = load()
+    require_device()
+    out = np.empty((T.shape[1], T.shape[1]))
+    check(lib.fastfp_tnt(device, T.shape[0], T.shape[1], _vp(Nvec), _vp(T), _vp(ph) if ph is not None else None,
+                         _vp(out), C.c_void_p(stream)))
+    return out
 
 
 def xcy(Nvec, T, sigma, x, y, device: int = 0, stream: int = 0) -> float:

@@ -508,6 +508,36 @@ int fastfp_xcy_blockn(int device, int64_t n, int64_t m, const double* Nvec, cons
   return xcy_run(device, n, m, Nvec, T, sigma, xw, yw, x, out, stream);
 }
 
+int fastfp_tnt(int device, int64_t n, int64_t m, const double* Nvec, const double* T, const double* phiinv,
+               double* out, void* stream) {
+  if (n < 1 || m < 1 || !Nvec || !T || !out) {
+    set_error("fastfp_tnt: null argument or non-positive size");
+    return FASTFP_ERR_INVALID;
+  }
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select CUDA device " + std::to_string(device)); return FASTFP_ERR_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(64, n / 256));
+  const size_t tot = (size_t)(n + n * m + m + m * m) + (size_t)nsplit * m * m;
+  double* d = nullptr;
+  FFP_CUDA(cudaMalloc(&d, tot * 8));
+  double *dN = d, *dT = dN + n, *dP = dT + n * m, *dO = dP + m, *dW = dO + m * m;
+  cudaError_t e = cudaMemcpyAsync(dN, Nvec, n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dT, T, n * m * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && phiinv) e = cudaMemcpyAsync(dP, phiinv, m * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dW, 0, (size_t)nsplit * m * m * 8, st);
+  int rc = 0;
+  if (e != cudaSuccess) rc = cuda_fail(e, "fastfp_tnt upload");
+  if (!rc) rc = launch_tnt(n, m, dN, dT, phiinv ? dP : nullptr, dW, nsplit, dO, st);
+  if (!rc) {
+    e = cudaMemcpyAsync(out, dO, m * m * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "fastfp_tnt download");
+  }
+  cudaFree(d);
+  return rc;
+}
+
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms) {
   if (!tflops || !ms || iters < 1 || kind < 0 || kind > 12) {
     set_error("fastfp_fp64_peak: invalid argument");

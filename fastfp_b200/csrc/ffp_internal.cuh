@@ -182,6 +182,8 @@ int launch_reduce_terms(const double* d_terms, int P, int64_t F, double* d_out, 
 bool sweep_config(int m, KernelCfg* cfg);
 int sweep_max_slab_doubles();
 // xcy.cu
+int launch_tnt(int64_t n, int64_t m, const double* dN, const double* dT, const double* d_phiinv, double* d_part,
+               int nsplit, double* d_out, cudaStream_t st);
 int launch_xcy(int64_t n, int64_t m, const double* dN, const double* dT, const double* dS,
                const double* dx, const double* dy, const double* dx0, double* d_work, double* d_out,
                cudaStream_t st);  // dx0: raw x for the x^T N^-1 y term (null: dx)

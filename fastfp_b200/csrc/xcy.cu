@@ -105,4 +105,64 @@ int launch_xcy(int64_t n, int64_t m, const double* dN, const double* dT, const d
   return 0;
 }
 
+// ---- TNT = T^T N^-1 T (+ diag(phiinv)) on the device: the matrices enterprise's pta.get_TNT /
+// get_phiinv hand to get_mats_fp / get_mats_nmfp (reference fastfp/utils.py:72-76, 97-99), for callers
+// that hold only the raw (Nvec, T, phi). Deterministic: the TOA axis is cut into fixed slices, each
+// (16 x 16 tile, slice) CTA accumulates its slice in order, a second kernel adds the slices in order.
+constexpr int TNT_TILE = 16, TNT_ROWS = 64;
+
+__global__ void __launch_bounds__(256) tnt_partial_kernel(int64_t n, int m, const double* __restrict__ Nvec,
+                                                          const double* __restrict__ T, double* __restrict__ part,
+                                                          int nsplit) {
+  __shared__ double A[TNT_ROWS][TNT_TILE + 1], B[TNT_ROWS][TNT_TILE + 1];
+  const int jb = blockIdx.x * TNT_TILE, kb = blockIdx.y * TNT_TILE, sp = blockIdx.z;
+  if (kb > jb) return;  // lower triangle of tiles; the reduce kernel mirrors it
+  const int tj = threadIdx.x / TNT_TILE, tk = threadIdx.x % TNT_TILE;
+  const int64_t per = (n + nsplit - 1) / nsplit, i0 = sp * per, i1 = min(n, i0 + per);
+  double acc = 0.0;
+  for (int64_t base = i0; base < i1; base += TNT_ROWS) {
+    for (int e = threadIdx.x; e < TNT_ROWS * TNT_TILE; e += 256) {
+      const int r = e / TNT_TILE, c = e % TNT_TILE;
+      const int64_t i = base + r;
+      double a = 0.0, b = 0.0;
+      if (i < i1) {
+        if (jb + c < m) a = T[i * m + jb + c] / Nvec[i];  // (T / Nvec) as enterprise forms it
+        if (kb + c < m) b = T[i * m + kb + c];
+      }
+      A[r][c] = a;
+      B[r][c] = b;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < TNT_ROWS; ++r) acc = fma(A[r][tj], B[r][tk], acc);
+    __syncthreads();
+  }
+  if (jb + tj < m && kb + tk < m) part[((size_t)sp * m + jb + tj) * m + kb + tk] = acc;
+}
+
+__global__ void tnt_reduce_kernel(int m, const double* __restrict__ part, int nsplit,
+                                  const double* __restrict__ phiinv, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * m) return;
+  const int j = idx / m, k = idx - j * m;
+  // tiles (jb, kb <= jb) were computed; take the lower triangle (k <= j) and mirror it, so the result is
+  // exactly symmetric (inside a diagonal tile (T_j/N) T_k and (T_k/N) T_j round differently)
+  const bool have = k <= j;
+  const int jj = have ? j : k, kk = have ? k : j;
+  double acc = 0.0;
+  for (int sp = 0; sp < nsplit; ++sp) acc += part[((size_t)sp * m + jj) * m + kk];
+  if (phiinv && j == k) acc += phiinv[j];
+  out[idx] = acc;
+}
+
+int launch_tnt(int64_t n, int64_t m, const double* dN, const double* dT, const double* d_phiinv, double* d_part,
+               int nsplit, double* d_out, cudaStream_t st) {
+  const unsigned nt = (unsigned)((m + TNT_TILE - 1) / TNT_TILE);
+  tnt_partial_kernel<<<dim3(nt, nt, (unsigned)nsplit), 256, 0, st>>>(n, (int)m, dN, dT, d_part, nsplit);
+  tnt_reduce_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, st>>>((int)m, d_part, nsplit, d_phiinv, d_out);
+  g_launches += 2;
+  FFP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace ffp

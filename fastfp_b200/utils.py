@@ -4,6 +4,8 @@
 * :func:`get_mats_fp` / :func:`get_mats_nmfp` -- ``fastfp/utils.py:57-101``: they only *collect*
   matrices from an ``enterprise`` PTA-like object (anything with ``get_phiinv``, ``get_TNT``,
   ``get_ndiag``, ``get_basis``); the return orders differ exactly as in the reference.
+* :func:`compute_TNTs` / :func:`compute_sigmas` -- device-side ``T^T N^-1 T (+ diag(phiinv))`` from the
+  raw basis (no reference counterpart, ``enterprise`` does this on the host).
 * :func:`initialize_pta` -- ``fastfp/utils.py:104-163`` needs the third-party ``enterprise``
   packages and is out of this engine's scope; it raises a clear
   error when they are absent.
@@ -43,6 +45,38 @@ def get_mats_nmfp(pta, noise):
     Nvecs = pta.get_ndiag(noise)
     Ts = pta.get_basis(noise)
     return TNTs, Nvecs, Ts
+
+
+def compute_TNTs(Nvecs, Ts, device: int = 0):
+    """``T^T N^-1 T`` per pulsar on the device -- what ``pta.get_TNT`` supplies to
+    :func:`get_mats_nmfp` (reference ``utils.py:97``) -- for callers that hold only the raw
+    ``(Nvec, T)``. A block-diagonal ``N`` (:class:`fastfp_b200.BlockNvec` / enterprise
+    ``ShermanMorrison``) is handled by its Sherman-Morrison correction on the host."""
+    from . import blockn
+
+    out = []
+    for Nvec, T in zip(Nvecs, Ts):
+        if blockn.is_block(Nvec):
+            T = np.asarray(T, dtype=np.float64)
+            B = blockn.BlockNvec(np.asarray(Nvec._nvec, dtype=np.float64), Nvec._slices, Nvec._jvec)
+            out.append(T.T @ B.solve(T))
+        else:
+            out.append(_cabi.tnt(Nvec, T, device=device))
+    return out
+
+
+def compute_sigmas(Nvecs, Ts, phiinvs, device: int = 0):
+    """``Sigma = T^T N^-1 T + diag(phiinv)`` per pulsar (reference ``utils.py:76``) from the raw
+    ``(Nvec, T, phiinv)``; the diagonal is added on the device for diagonal ``N``."""
+    from . import blockn
+
+    out = []
+    for Nvec, T, ph in zip(Nvecs, Ts, phiinvs):
+        if blockn.is_block(Nvec):
+            out.append(compute_TNTs([Nvec], [T], device=device)[0] + np.diag(np.asarray(ph, dtype=np.float64)))
+        else:
+            out.append(_cabi.tnt(Nvec, T, phiinv=ph, device=device))
+    return out
 
 
 def initialize_pta(*args, **kwargs):

@@ -147,6 +147,11 @@ int fastfp_nmfp_stage_ms(const fastfp_pack_t* pack, double* ms3);
  * x^T C^-1 y out, general (LU, partial pivoting) Sigma solve like jnp.linalg.solve. */
 int fastfp_xcy(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
                const double* sigma, const double* x, const double* y, double* out, void* stream);
+/* fastfp_tnt: TNT = T^T N^-1 T for diagonal N (host arrays; out is (m, m) row-major), plus
+ * diag(phiinv) when phiinv is not NULL -- i.e. the Sigma of get_mats_fp (fastfp/utils.py:76) or the
+ * TNT of get_mats_nmfp (fastfp/utils.py:97) for callers that hold only the raw basis. Deterministic. */
+int fastfp_tnt(int device, int64_t n, int64_t m, const double* Nvec, const double* T,
+               const double* phiinv, double* out, void* stream);
 /* the same inner product for a block-diagonal N = diag(Nvec) + epoch blocks: xw = (N^-1 x) * Nvec and
  * yw = (N^-1 y) * Nvec are prepared on the host (Sherman-Morrison), x is the raw vector; sigma is the
  * block-N Sigma. (The reference's get_xCy excludes this case, fastfp/utils.py:29-31.) */

@@ -174,3 +174,35 @@ def test_full_size_properties(cfg, F):
     tt, cond = truth.fp_sweep_truth(*args)
     got = fp.per_pulsar_terms(freqs[idx], *a)[sub]
     assert np.all(np.abs(got - tt.astype(float)) <= term_tolerance(tt.astype(float), cond, ora))
+
+
+@pytest.mark.parametrize("n,m", [(37, 3), (1000, 72), (5003, 150)])
+def test_device_tnt_and_sigma(n, m):
+    """T^T N^-1 T (+ diag phiinv) on the device against NumPy; deterministic."""
+    rng = np.random.default_rng(n + m)
+    T, Nvec = rng.standard_normal((n, m)), rng.uniform(0.5, 2.0, n) * 1e-13
+    ph = rng.uniform(1.0, 1e6, m)
+    want = T.T @ (T / Nvec[:, None])
+    scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
+    got = fastfp_b200.compute_TNTs([Nvec], [T])[0]
+    assert np.abs(got - want).max() <= 64 * EPS * scale.max()
+    np.testing.assert_array_equal(got, got.T)
+    np.testing.assert_array_equal(got, fastfp_b200.compute_TNTs([Nvec], [T])[0])
+    sig = fastfp_b200.compute_sigmas([Nvec], [T], [ph])[0]
+    np.testing.assert_array_equal(sig, got + np.diag(ph))
+
+
+def test_pack_from_device_built_sigmas_matches_goldens(golden):
+    """The whole precompute on the device: Sigma from the raw (Nvec, T, phiinv), then the sweep. Sigma
+    differs from the golden one by summation-order rounding only, so the result stays inside the same
+    envelope as the direct test above."""
+    g = golden("fp_red")
+    Nvecs, Ts, sigmas = _args(g)
+    phiinvs = [np.diag(s) - np.diag(T.T @ (T / N[:, None])) for s, T, N in zip(sigmas, Ts, Nvecs)]
+    sig = fastfp_b200.compute_sigmas(Nvecs, Ts, phiinvs)
+    for a, b in zip(sig, sigmas):
+        assert np.abs(a - b).max() <= 256 * EPS * np.abs(b).max()
+    got = fastfp_b200.FastFp(g.psrs)(g["freqs"], Nvecs, Ts, sig)
+    ora_terms = o.fp_sweep(g["freqs"], g.lst("toas"), g.lst("res"), Nvecs, Ts, sigmas, per_pulsar=True)
+    tol = term_tolerance(g["truth_terms"], g["cond"], ora_terms)
+    assert np.all(np.abs(got - g["ref_fp"]) <= 1e-10 * np.abs(g["ref_fp"]) + 4 * tol.sum(0))
