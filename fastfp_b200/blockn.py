@@ -55,12 +55,28 @@ class BlockNvec:
         nvec = np.asarray(self.nvec, dtype=np.float64)
         X = np.asarray(X, dtype=np.float64)
         out = X / (nvec if X.ndim == 1 else nvec[:, None])
-        for sl, j in zip(self.slices, self.jvec):
-            ninv = 1.0 / nvec[sl]
-            beta = j / (1.0 + j * ninv.sum())
-            corr = beta * (out[sl].sum(axis=0))
-            out[sl] = out[sl] - (ninv * corr if X.ndim == 1 else ninv[:, None] * corr)
+        idx, eid, offs = _epoch_index(self.slices)
+        if idx.size:
+            ninv = 1.0 / nvec
+            jv = np.asarray(self.jvec, dtype=np.float64)
+            beta = jv / (1.0 + jv * np.add.reduceat(ninv[idx], offs))
+            sums = np.add.reduceat(out[idx], offs, axis=0)  # per-epoch sums of N_d^-1 X
+            corr = (beta * sums if X.ndim == 1 else beta[:, None] * sums)[eid]
+            out[idx] -= ninv[idx] * corr if X.ndim == 1 else ninv[idx, None] * corr
         return out
+
+
+def _epoch_index(slices):
+    """Concatenated TOA indices of all epochs, the epoch id of each, and the start offsets."""
+    if len(slices) == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z
+    starts = np.asarray([int(s.start) for s in slices], dtype=np.int64)
+    lens = np.asarray([int(s.stop) - int(s.start) for s in slices], dtype=np.int64)
+    offs = np.cumsum(lens) - lens
+    eid = np.repeat(np.arange(len(slices), dtype=np.int64), lens)
+    idx = np.arange(int(lens.sum()), dtype=np.int64) - offs[eid] + starts[eid]
+    return idx, eid, offs
 
 
 def is_block(Nvec) -> bool:
@@ -89,10 +105,11 @@ def prepare(toas, res, Nvec, T, CI: int):
     # Sherman-Morrison applied to T and r, expressed as (N^-1 x) * nvec so the kernels' x/N recovers it
     Tw, rw = T.copy(), res.copy()
     beta = np.zeros(len(slices))
-    for e, ((a, b), j) in enumerate(zip(slices, jvec)):
-        beta[e] = j / (1.0 + j * ninv[a:b].sum())
-        Tw[a:b] -= beta[e] * (T[a:b] * ninv[a:b, None]).sum(axis=0)
-        rw[a:b] -= beta[e] * (res[a:b] * ninv[a:b]).sum()
+    if slices:
+        idx, eid, offs = _epoch_index([slice(a, b) for a, b in slices])
+        beta = jvec / (1.0 + jvec * np.add.reduceat(ninv[idx], offs))
+        Tw[idx] -= (beta[:, None] * np.add.reduceat(T[idx] * ninv[idx, None], offs, axis=0))[eid]
+        rw[idx] -= (beta * np.add.reduceat(res[idx] * ninv[idx], offs))[eid]
     # groups of TOAs: epochs (padded to multiples of 4) then the uncovered TOAs, 4 at a time
     KB = CI // 4
     order: List[int] = []          # original TOA index or -1 (padding), length 4 * number of k-blocks
