@@ -224,6 +224,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   while (!mbar_try_wait(bar, parity)) __nanosleep(64);  // back off: polling shares the MIO queue with LDS
 }
+// for the warps on the critical path (the MMA consumers): try_wait already suspends the warp for a
+// hardware-chosen interval and wakes it when the phase completes, so no extra sleep that could overshoot
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -300,8 +300,8 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
     double a0[NMBW], b0[NNB];
     {
       const uint32_t k = g;
-      mbar_wait(&sm.g_full[k % C::GST], (k / C::GST) & 1u);
-      mbar_wait(&sm.s_full[k % C::SST], (k / C::SST) & 1u);
+      mbar_wait_spin(&sm.g_full[k % C::GST], (k / C::GST) & 1u);
+      mbar_wait_spin(&sm.s_full[k % C::SST], (k / C::SST) & 1u);
       const double* gt = sm.Gring + (k % C::GST) * C::GT + (wm * NMBW) * 32 + lane;
       const double* sb = sm.Sring + (k % C::SST) * C::ST + (wn * NNB) * 32 + bperm;
 #pragma unroll
@@ -328,8 +328,8 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
           for (int q = 0; q < NNB; ++q) b1[q] = sb[((kb + 1) * C::NBT + q) * 32];
         } else if (c + 1 < nch) {
           const uint32_t k1 = k + 1;
-          mbar_wait(&sm.g_full[k1 % C::GST], (k1 / C::GST) & 1u);
-          mbar_wait(&sm.s_full[k1 % C::SST], (k1 / C::SST) & 1u);
+          mbar_wait_spin(&sm.g_full[k1 % C::GST], (k1 / C::GST) & 1u);
+          mbar_wait_spin(&sm.s_full[k1 % C::SST], (k1 / C::SST) & 1u);
           const double* gt1 = sm.Gring + (k1 % C::GST) * C::GT + (wm * NMBW) * 32 + lane;
           const double* sb1 = sm.Sring + (k1 % C::SST) * C::ST + (wn * NNB) * 32 + bperm;
 #pragma unroll

@@ -494,8 +494,8 @@ __global__ void __launch_bounds__(StageBCfg<NMBV>::THREADS, 1) nmfp_stageB_kerne
 
   for (int it = 0; it < nit; ++it) {
     const int p = it / nd, dl = it - p * nd, buf = p & 1, s = it % NS;
-    if (dl == 0) mbar_wait(&zfull[buf], (p >> 1) & 1);
-    mbar_wait(&lfull[s], (it / NS) & 1);
+    if (dl == 0) mbar_wait_spin(&zfull[buf], (p >> 1) & 1);
+    mbar_wait_spin(&lfull[s], (it / NS) & 1);
     const double* zt = Zb + (buf * NH + h) * ZT + wl * 32 + bperm;
     const double* lt = Lb + s * LFW;
     double acc[NMBV][2];
