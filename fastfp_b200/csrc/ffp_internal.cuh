@@ -25,9 +25,17 @@ constexpr int MAX_M = 320;     // widest basis the sweep kernel handles
 // owns NMBW row blocks (8 basis rows each) x NNB column blocks (8 columns = 4 frequencies x
 // {sin, cos}); WMW consumer warps split the rows, NWC/WMW split the frequencies of the tile.
 //   CI  TOAs per staged chunk (KB = CI/4 k-blocks)
-template <int NMBW_, int NNB_, int WMW_, int CI_>
+//   NWC / NWP  consumer (MMA) / producer (sincos) warps of the CTA. The MMA issue rate of one warp is
+//   limited, so narrow accumulator tiles want three consumer warps per SM sub-partition (12 + 8);
+//   the default is two per sub-partition and four producer warps per sub-partition (8 + 16).
+template <int NMBW_, int NNB_, int WMW_, int CI_, int NWC_ = ffp::NWC, int NWP_ = ffp::NWP>
 struct SweepCfg {
   static constexpr int NMBW = NMBW_, NNB = NNB_, WMW = WMW_, CI = CI_;
+  static constexpr int NWC = NWC_, NWP = NWP_, NTC = NWC_ * 32, NTP = NWP_ * 32, NTHREADS = NTC + NTP;
+  // setmaxnreg split of the launch-time register pool (NTHREADS x the launch register count)
+  static constexpr int CREGS = NWC_ == 8 ? CONSUMER_REGS : 112, PREGS = NWC_ == 8 ? PRODUCER_REGS : 64;
+  static_assert(NTHREADS <= 1024 && NWC % WMW_ == 0, "warp layout");
+  static_assert(NTC * CREGS + NTP * PREGS <= NTHREADS * ((65536 / NTHREADS) / 8 * 8), "register pool");
   static constexpr int WNW = NWC / WMW;        // consumer warps along frequency
   static constexpr int KF = WNW * NNB * 4;     // frequencies per CTA
   static constexpr int NBT = KF / 4;           // column blocks per CTA tile
@@ -85,12 +93,14 @@ struct PulsarMeta {
 
 struct KernelCfg {  // run-time mirror of SweepCfg's parameters
   int nmbw, nnb, wmw, ci;
-  int kf() const { return (NWC / wmw) * nnb * 4; }
+  int nwc = NWC;  // consumer warps (8, or 12 for the three-row-group configurations)
+  int kf() const { return (nwc / wmw) * nnb * 4; }
   int mp() const { return 8 * nmbw * wmw; }
   bool operator<(const KernelCfg& o) const {
     if (nmbw != o.nmbw) return nmbw < o.nmbw;
     if (nnb != o.nnb) return nnb < o.nnb;
     if (wmw != o.wmw) return wmw < o.wmw;
+    if (nwc != o.nwc) return nwc < o.nwc;
     return ci < o.ci;
   }
 };

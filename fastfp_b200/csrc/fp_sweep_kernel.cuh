@@ -105,13 +105,13 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
   constexpr int CI = C::CI, XW = C::XW;
   const int tidp = pw * 32 + lane;
   const int bk = lane & 3, bf8 = lane >> 2;
-  const int bx0 = C::NX >= NWP ? pw * XW : pw % C::NX;         // first group of 8 frequencies
-  const int bkb0 = C::NX >= NWP ? 0 : (pw / C::NX) * C::KBW;   // first k-block
-  const int bsplit = C::NX >= NWP ? 0 : pw / C::NX;
+  const int bx0 = C::NX >= C::NWP ? pw * XW : pw % C::NX;         // first group of 8 frequencies
+  const int bkb0 = C::NX >= C::NWP ? 0 : (pw / C::NX) * C::KBW;   // first k-block
+  const int bsplit = C::NX >= C::NWP ? 0 : pw / C::NX;
   // element (frequency group x, k-block kb) -> S offset (kb*NBT + 2*x + (bf8>>2))*32 + 8*(bf8&3) + 2*bk:
   // the (sin, cos) pair of a (TOA, frequency) is adjacent, so it goes out as one 16-byte store
   const int sofs = (bf8 >> 2) * 32 + 8 * (bf8 & 3) + 2 * bk;
-  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + (size_t)C::NACCX * NTC + tidp;
+  double* const sl = ar.slab + (size_t)blockIdx.x * C::SLAB + (size_t)C::NACCX * C::NTC + tidp;
   uint32_t g = 0;
   for (;;) {
     __syncthreads();  // B1: work item published
@@ -214,7 +214,7 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
         for (int xx = 0; xx < XW; ++xx)
 #pragma unroll
           for (int q = 0; q < 5; ++q) {
-            double* a = sl + (size_t)(xx * 5 + q) * NTP;
+            double* a = sl + (size_t)(xx * 5 + q) * C::NTP;
             if (flushed) atomicAdd(a, s2[xx][q]);  // result unused -> RED.ADD.F64, no round trip
             else __stcg(a, s2[xx][q]);
             s2[xx][q] = 0.0;
@@ -230,7 +230,7 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
         double v = s2[xx][q];
-        if (flushed) v += __ldcg(sl + (size_t)(xx * 5 + q) * NTP);
+        if (flushed) v += __ldcg(sl + (size_t)(xx * 5 + q) * C::NTP);
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         s2[xx][q] = v;
@@ -383,7 +383,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
               // the slot is private to this thread: first block stores, later blocks add with a
               // fire-and-forget reduction (RED.ADD.F64) -- a load/add/store chain would expose one L2
               // round trip per accumulator
-              double* a = sl + (size_t)((r * NNB + q) * 2 + e) * NTC;
+              double* a = sl + (size_t)((r * NNB + q) * 2 + e) * C::NTC;
               if (flushed) atomicAdd(a, acc[r][q][e]);
               else __stcg(a, acc[r][q][e]);
               acc[r][q][e] = 0.0;
@@ -393,7 +393,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
           for (int q = 0; q < NNB; ++q)
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-              double* a = sl + (size_t)(C::NACC + q * 3 + e) * NTC;
+              double* a = sl + (size_t)(C::NACC + q * 3 + e) * C::NTC;
               if (flushed) atomicAdd(a, es[q][e]);
               else __stcg(a, es[q][e]);
               es[q][e] = 0.0;
@@ -413,12 +413,12 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
         for (int q = 0; q < NNB; ++q)
 #pragma unroll
           for (int e = 0; e < 2; ++e)
-            if (!(ECORR && r == NMBW - 1 && slot_warp)) acc[r][q][e] += __ldcg(sl + (size_t)((r * NNB + q) * 2 + e) * NTC);
+            if (!(ECORR && r == NMBW - 1 && slot_warp)) acc[r][q][e] += __ldcg(sl + (size_t)((r * NNB + q) * 2 + e) * C::NTC);
       if (ECORR && slot_warp) {
 #pragma unroll
         for (int q = 0; q < NNB; ++q)
 #pragma unroll
-          for (int e = 0; e < 3; ++e) es[q][e] += __ldcg(sl + (size_t)(C::NACC + q * 3 + e) * NTC);
+          for (int e = 0; e < 3; ++e) es[q][e] += __ldcg(sl + (size_t)(C::NACC + q * 3 + e) * C::NTC);
       }
     }
     // this thread holds Y[row][freq] for rows 8*(wm*NMBW + r) + (lane>>2) and the tile frequencies
@@ -509,24 +509,24 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
 }
 
 template <class C, bool NMFP, bool ECORR>
-__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fp_sweep_kernel(const SweepArgs ar) {
+__global__ void __launch_bounds__(C::NTHREADS, CTAS_PER_SM) fp_sweep_kernel(const SweepArgs ar) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SweepSmem<C> sm(smem_raw);
   __shared__ int s_work;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < C::SST; ++s) { mbar_init(&sm.s_full[s], NWP); mbar_init(&sm.s_empty[s], NWC); }
-    for (int s = 0; s < C::GST; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], NWC); }
-    for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], NWP); }
+    for (int s = 0; s < C::SST; ++s) { mbar_init(&sm.s_full[s], C::NWP); mbar_init(&sm.s_empty[s], C::NWC); }
+    for (int s = 0; s < C::GST; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], C::NWC); }
+    for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], C::NWP); }
     fence_barrier_init();
   }
   __syncthreads();
-  if (wid < NWC) {
-    reg_alloc<CONSUMER_REGS>();
+  if (wid < C::NWC) {
+    reg_alloc<C::CREGS>();
     consumer_loop<C, NMFP, ECORR>(ar, sm, &s_work, wid, lane);
   } else {
-    reg_dealloc<PRODUCER_REGS>();
-    producer_loop<C, NMFP, ECORR>(ar, sm, &s_work, wid - NWC, lane);
+    reg_dealloc<C::PREGS>();
+    producer_loop<C, NMFP, ECORR>(ar, sm, &s_work, wid - C::NWC, lane);
   }
 }
 
@@ -549,7 +549,7 @@ int launch_sweep_cfg(const fastfp_pack* pk, const Group& g, const SweepArgs& bas
   const int64_t resident = (int64_t)CTAS_PER_SM * pk->num_sms;
   const unsigned grid = (unsigned)(nwork < resident ? nwork : resident);
   FFP_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
-  fp_sweep_kernel<C, NMFP, ECORR><<<grid, NTHREADS, C::SMEM, st>>>(a);
+  fp_sweep_kernel<C, NMFP, ECORR><<<grid, C::NTHREADS, C::SMEM, st>>>(a);
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
   return 0;
@@ -561,9 +561,11 @@ int dispatch_sweep_w2(const fastfp_pack*, const Group&, const SweepArgs&, bool n
 int dispatch_sweep_w4(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 int dispatch_sweep_wide(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 
-#define FFP_SWEEP_CASE(NMBWv, NNBv, WMWv, CIv)                                                     \
-  if (g.cfg.nmbw == NMBWv && g.cfg.nnb == NNBv && g.cfg.wmw == WMWv && g.cfg.ci == CIv) {           \
-    using Cfg_ = SweepCfg<NMBWv, NNBv, WMWv, CIv>;                                                  \
+#define FFP_SWEEP_CASE(NMBWv, NNBv, WMWv, CIv) FFP_SWEEP_CASE_W(NMBWv, NNBv, WMWv, CIv, 8, 16)
+#define FFP_SWEEP_CASE_W(NMBWv, NNBv, WMWv, CIv, NWCv, NWPv)                                       \
+  if (g.cfg.nmbw == NMBWv && g.cfg.nnb == NNBv && g.cfg.wmw == WMWv && g.cfg.ci == CIv &&          \
+      g.cfg.nwc == NWCv) {                                                                         \
+    using Cfg_ = SweepCfg<NMBWv, NNBv, WMWv, CIv, NWCv, NWPv>;                                      \
     if (pk->ecorr) return nmfp ? launch_sweep_cfg<Cfg_, true, true>(pk, g, a, st)                   \
                                : launch_sweep_cfg<Cfg_, false, true>(pk, g, a, st);                 \
     return nmfp ? launch_sweep_cfg<Cfg_, true, false>(pk, g, a, st)                                 \

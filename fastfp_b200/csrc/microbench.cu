@@ -223,6 +223,46 @@ __global__ void __launch_bounds__(256) dmma_16816_kernel(int iters, double seed,
   if (s == 12345.678) sink[0] = s;
 }
 
+// kinds 13-15: the sweep kernel's warp specialisation in isolation, registers only: 8 warps issue DMMAs
+// (two per sub-partition, 8 independent accumulators each), 16 warps issue independent DFMA chains, with
+// the DFMA warps asking for RATIO/256 of the pipe time the DMMA warps ask for. What the shared pipe
+// delivers for such a mix is the practical ceiling of any kernel that needs both instruction kinds.
+template <int RATIO256>
+__global__ void __launch_bounds__(768, 1) warp_mix_kernel(int iters, double seed, double* sink) {
+  const int w = threadIdx.x >> 5;
+  double s = 0;
+  if (w < 8) {
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = seed + k;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[k][0]), "+d"(c[k][1])
+                     : "d"(a), "d"(b));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+  } else {
+    // per iteration a DMMA warp occupies the pipe 8 x 16 = 128 cycles of its sub-partition, a DFMA warp
+    // 16 x 2 = 32; two DMMA warps and four DFMA warps per sub-partition -> 256 : 128 per common iteration
+    const int itf = (int)((long long)iters * 2 * RATIO256 / 256);
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = seed + k + threadIdx.x * 1e-3;
+    const double x = 1.0000001, y = 1e-9;
+    for (int it = 0; it < itf; ++it) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+  }
+  if (s == 12345.678) sink[0] = s;
+}
+
 int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
   int dev = 0, sms = 0;
   FFP_CUDA(cudaGetDevice(&dev));
@@ -265,6 +305,9 @@ int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
     else if (kind == 10) dmma_tile_kernel<9, 2><<<sms, 512>>>(iters, 1.0, sink);   // 4 warps / sub-partition
     else if (kind == 11) dmma_tile_kernel<9, 4><<<sms, 128>>>(iters, 1.0, sink);   // 1 warp / sub-partition
     else if (kind == 12) dmma_16816_kernel<<<sms, 256>>>(iters, 1.0, sink);
+    else if (kind == 13) warp_mix_kernel<32><<<sms, 768>>>(iters, 1.0, sink);   // DFMA asks for 1/8 of DMMA's pipe time
+    else if (kind == 14) warp_mix_kernel<50><<<sms, 768>>>(iters, 1.0, sink);   // ~0.195 (the sweep kernel's mix)
+    else if (kind == 15) warp_mix_kernel<96><<<sms, 768>>>(iters, 1.0, sink);   // 3/8
     else if (kind == 3) outer_peak_kernel<false><<<sms * 2, 128>>>(iters, 1.0, sink);
     else outer_peak_kernel<true><<<sms * 2, 128>>>(iters, 1.0, sink);
     FFP_CUDA(cudaEventRecord(e1));
@@ -282,6 +325,9 @@ int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
                            : kind == 10 ? (double)sms * 16 * 2 * 18 * 256.0 * iters
                            : kind == 11 ? (double)sms * 4 * 2 * 36 * 256.0 * iters
                            : kind == 12 ? (double)sms * 8 * 4 * 2048.0 * iters
+                           : kind >= 13 && kind <= 15
+                               ? (double)sms * (8 * 8 * 256.0 * iters +
+                                                16 * 32 * 16.0 * (double)((long long)iters * 2 * (kind == 13 ? 32 : kind == 14 ? 50 : 96) / 256))
                            : kind == 2 ? (double)grid * (256 * 16.0 + 8 * 4.0 * 256.0) * iters
                                        : (double)sms * 2 * 128 * 144.0 * iters;
   *tflops = 2.0 * fma_count / (best * 1e-3) / 1e12;

@@ -162,7 +162,9 @@ int fastfp_xcy_blockn(int device, int64_t n, int64_t m, const double* Nvec, cons
 /* ---- measurement helper ----------------------------------------------------------------
  * fastfp_fp64_peak: times a dependent-chain-free DFMA loop (kind 0) or DMMA m8n8k4 loop
  * (kind 1), or both interleaved (kind 2), on the device and returns TFLOP/s; bench.py uses
- * kind 0 as the measured fp64-pipe denominator (MEASURED_PEAKS.json has no fp64 figure). */
+ * kind 1 as the measured fp64-pipe denominator (MEASURED_PEAKS.json has no fp64 figure). Kinds 3-12
+ * are the kernel-design probes of csrc/microbench.cu; 13-15 run the sweep kernel's warp
+ * specialisation (8 DMMA warps + 16 DFMA warps) on registers only. */
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms);
 
 #ifdef __cplusplus
