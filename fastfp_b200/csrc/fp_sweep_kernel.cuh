@@ -443,7 +443,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
             // 32-frequency tile, MMA B-fragment order: k-block (row/4), column block (4 freqs), then
             // position 16*sc + 4*(freq%4) + row%4 -- the layout stage B loads without conflicts
             const int64_t nt32 = (ar.F + 31) >> 5;
-            const int jr = j - mfix, fi = (int)(f & 31);
+            const int jr = j - mfix + (ar.mvmax - pm.mvar), fi = (int)(f & 31);  // rows follow the top padding
             double* z = ar.Z + ((size_t)p * nt32 + (f >> 5)) * ((size_t)ar.mvmax * 64) +
                         (size_t)(((jr >> 2) * 8 + (fi >> 2)) * 32 + 4 * (fi & 3) + (jr & 3));
             z[0] = ys;

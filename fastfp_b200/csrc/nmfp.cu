@@ -50,22 +50,28 @@ __global__ void nmfp_init_sigma_kernel(double* __restrict__ Lbuf, const PulsarMe
   }
 }
 
-// S0[p] (padded to mvpad, identity on the padding) and z'_r[p] out of the partially factored matrix
+// S0[p] and z'_r[p] out of the partially factored matrix, padded to mvpad. The padding (identity rows and
+// columns, zeros in z') sits at the TOP-LEFT: L^-1 of diag(I, S) is diag(I, L_S^-1), so the leading
+// (mvpad - mvar) columns of L^-1 only ever multiply zeros and stage B skips their k-blocks entirely --
+// with the padding at the bottom the same blocks would be spread over every block row and none could go.
 __global__ void nmfp_extract_kernel(const double* __restrict__ Lbuf, const PulsarMeta* __restrict__ meta,
                                     const double* __restrict__ ur, double* __restrict__ S0,
                                     double* __restrict__ zr, int mvpad) {
   const PulsarMeta pm = meta[blockIdx.x];
-  const int m = pm.m, mf = pm.mfix, mv = pm.mvar;
+  const int m = pm.m, mf = pm.mfix, mv = pm.mvar, pad = mvpad - mv;
   const double* A = Lbuf + pm.L_off;
   double* S = S0 + (size_t)blockIdx.x * mvpad * mvpad;
   for (int idx = threadIdx.x; idx < mvpad * mvpad; idx += blockDim.x) {
     const int i = idx / mvpad, j = idx - i * mvpad;
     double v = i == j ? 1.0 : 0.0;
-    if (i < mv && j < mv) v = i >= j ? A[(size_t)(mf + i) * m + mf + j] : A[(size_t)(mf + j) * m + mf + i];
+    if (i >= pad && j >= pad) {
+      const int ii = i - pad, jj = j - pad;
+      v = ii >= jj ? A[(size_t)(mf + ii) * m + mf + jj] : A[(size_t)(mf + jj) * m + mf + ii];
+    }
     S[idx] = v;
   }
   for (int k = threadIdx.x; k < mvpad; k += blockDim.x)
-    zr[(size_t)blockIdx.x * mvpad + k] = k < mv ? ur[(size_t)blockIdx.x * MAX_M + mf + k] : 0.0;
+    zr[(size_t)blockIdx.x * mvpad + k] = k >= pad ? ur[(size_t)blockIdx.x * MAX_M + mf + k - pad] : 0.0;
 }
 
 int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res, const double* d_Nvec,
@@ -294,9 +300,10 @@ __global__ void __launch_bounds__(FactorCfg<NMBV>::FW * 32, FactorCfg<NMBV>::CTA
 #pragma unroll
     for (int j = 0; j <= i; ++j) {
       double2 t = __ldg(reinterpret_cast<const double2*>(S + (size_t)(8 * i + R) * MV + 8 * j + 2 * q));
-      if (i == j && 8 * i + R < pm.mvar) {
-        if (R == 2 * q) t.x += ph[8 * i + R];
-        if (R == 2 * q + 1) t.y += ph[8 * i + R];
+      if (i == j && 8 * i + R >= MV - pm.mvar) {  // real rows follow the top padding
+        const double pv = ph[8 * i + R - (MV - pm.mvar)];
+        if (R == 2 * q) t.x += pv;
+        if (R == 2 * q + 1) t.y += pv;
       }
       st_c(blk(i, j), t.x, t.y);
     }
@@ -409,6 +416,7 @@ struct StageBArgs {
   const double* A;       // [P][nt32][160]     a_ss | a_sc | a_cc | a_sr | a_cr, 32 frequencies each
   const double* lf;      // [Db][P][lfw]       L^-1 fragments + v
   const double* freqs;   // [F]
+  const PulsarMeta* meta;  // per pulsar: mvar -> leading padding k-blocks that are skipped
   double* out;           // [D][F]  (this launch writes rows d0 .. d0+Db-1)
   int64_t F, out_ld;
   int P, nt32, Db, lfw;
@@ -491,6 +499,7 @@ __global__ void __launch_bounds__(StageBCfg<NMBV>::THREADS, 1) nmfp_stageB_kerne
   static_assert(NB_DT == 8, "lane >> 2 indexes the draw inside a CTA");
   double fpacc = 0.0;
   double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0, k4 = 0.0;
+  int kb0 = 0;
 
   for (int it = 0; it < nit; ++it) {
     const int p = it / nd, dl = it - p * nd, buf = p & 1, s = it % NS;
@@ -498,16 +507,19 @@ __global__ void __launch_bounds__(StageBCfg<NMBV>::THREADS, 1) nmfp_stageB_kerne
     mbar_wait_spin(&lfull[s], (it / NS) & 1);
     const double* zt = Zb + (buf * NH + h) * ZT + wl * 32 + bperm;
     const double* lt = Lb + s * LFW;
+    if (dl == 0) kb0 = (8 * NMBV - ar.meta[p].mvar) >> 2;  // k-blocks that only see the top padding
     double acc[NMBV][2];
 #pragma unroll
     for (int mb = 0; mb < NMBV; ++mb) acc[mb][0] = acc[mb][1] = 0.0;
 #pragma unroll
     for (int kb = 0; kb < KBV; ++kb) {
-      const double b = zt[kb * 8 * 32];
-      const int off = linv_block_off(NMBV, kb);
+      if (kb >= kb0) {  // warp-uniform
+        const double b = zt[kb * 8 * 32];
+        const int off = linv_block_off(NMBV, kb);
 #pragma unroll
-      for (int mb = kb / 2; mb < NMBV; ++mb)
-        dmma884(acc[mb][0], acc[mb][1], lt[(off + mb - kb / 2) * 32 + lane], b);
+        for (int mb = kb / 2; mb < NMBV; ++mb)
+          dmma884(acc[mb][0], acc[mb][1], lt[(off + mb - kb / 2) * 32 + lane], b);
+      }
     }
     // u = L^-1 z' for row 8*mb + (lane>>2), frequency fi: [0] = sin, [1] = cos
     const double* v = lt + nblk * 32;
@@ -642,7 +654,7 @@ int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, con
     marks.mark(0, st);
     for (int64_t dd = 0; dd < D; dd += DB) {
       const int Db = (int)std::min(DB, D - dd);
-      StageBArgs sb{dZ, dA, dLf, d_freqs + f0, d_out + dd * F + f0, Fb, F, P, nt32, Db, lfw};
+      StageBArgs sb{dZ, dA, dLf, d_freqs + f0, pk->d_meta, d_out + dd * F + f0, Fb, F, P, nt32, Db, lfw};
       const double* ph = d_phiinv_var + dd * pk->mvar_total;
       int rc;
       if (NMBV == 4) rc = run_factor_and_stageB<4>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
