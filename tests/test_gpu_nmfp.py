@@ -176,3 +176,38 @@ def test_nmfp_full_size_properties():
     well = freqs > 40 / pta.Tspan
     assert np.abs(full[3][well] / fp[well] - 1).max() < 1e-9
     assert np.abs(full[3] / fp - 1).max() < 1e-5
+
+
+def test_nmfp_mixed_per_draw_widths_in_one_pack():
+    """Pulsars with different numbers of red-noise components share one pack: the per-draw blocks are
+    padded to the widest one (each at its own top-left offset) and stage B skips a different number of
+    leading k-blocks per pulsar."""
+    import copy
+
+    parts = [synth.make_pta(2, [260, 301], n_tm=[3, 5], ncomps=5, seed=41, inc_cp=False),
+             synth.make_pta(2, [333, 280], n_tm=[4, 2], ncomps=14, seed=42, inc_cp=False)]
+    psrs, Nvecs, Ts, TNTs, sigs, phi_args = [], [], [], [], [], []
+    for k, pta in enumerate(parts):
+        for p, q in enumerate(pta.psrs):
+            q = copy.copy(q)
+            q.name = f"{q.name}_{k}"  # the two synthetic sets reuse names
+            psrs.append(q)
+            Nvecs.append(pta.Nvecs[p]); Ts.append(pta.Ts[p]); TNTs.append(pta.TNTs[p])
+            sigs.append(RN_container(q, Ffreqs=pta.Ffreqs))
+            phi_args.append(dict(psr_name=q.name, n_tm=pta.n_tm[p], Ffreqs=pta.Ffreqs))
+    D, F = 9, 37
+    rng = np.random.default_rng(3)
+    samples = {}
+    for q in psrs:
+        samples[f"{q.name}_red_noise_log10_A"] = rng.uniform(-15.0, -13.0, D)
+        samples[f"{q.name}_red_noise_gamma"] = rng.uniform(1.0, 6.0, D)
+    freqs = np.sort(rng.uniform(2e-9, 3e-7, F))
+    got = NMFP(psrs, sigs)(freqs, samples, Nvecs, Ts, TNTs)
+    assert got.shape == (D, F)
+    toas, res = [q.toas for q in psrs], [q.residuals for q in psrs]
+    for d in (0, 4, D - 1):
+        pars = {k: v[d] for k, v in samples.items()}
+        sig = o.get_sigmas(pars, TNTs, phi_args)
+        tt, cond = truth.fp_sweep_truth(freqs, toas, res, Nvecs, Ts, sig)
+        tv = tt.sum(0).astype(float)
+        assert np.all(np.abs(got[d] - tv) <= _tol(tv, cond.sum(0))), d
