@@ -343,7 +343,7 @@ def run_nmfp(args, wl, rank, world, local):
         ach_b = evals_rank * fl_b / (stage[2] * 1e-3) / 1e12
         ach_all = evals_rank * fl_total / (stage.sum() * 1e-3) / 1e12
         ach_gbs = evals_rank * bytes_per_eval(wl["n"], M_BASIS) / (stage.sum() * 1e-3) / 1e9
-        nmfp_traffic = 1.596071e9 + 12.80512e6 if (F, hi - lo) == (1000, 1000) else None  # ncu, C3 shapes only
+        nmfp_traffic = 1.595419e9 + 12.058112e6 if (F, hi - lo) == (1000, 1000) else None  # ncu, C3 shapes only
         line = {
             "metric": "Fp evals/sec (freqs x pulsars x draws)", "value": evals_step / ms_step * 1e3,
             "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -373,7 +373,7 @@ def run_nmfp(args, wl, rank, world, local):
                          "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
                                         "MEASURED_PEAKS.json holds no fp64 figure",
                          "note": "algorithmic flops 2 mv^2 + 10 mv per eval for stage B (exact triangle, mv = 60); the "
-                                 "kernel executes 72 8x4 blocks per 4 frequencies against 57 for the exact triangle"},
+                                 "kernel executes 64 8x4 blocks per 4 frequencies against 57 for the exact triangle"},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
                              "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference re-streams every input "
