@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the Fp frequency-sweep hot path (BASELINE.json metric: Fp evals/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4]  (T = tiny, contract tests only) [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one sweep of the plain-Fp statistic over the rank's frequency shard for all pulsars
@@ -44,6 +44,7 @@ WORKLOADS = {
     "C2": dict(P=45, n=5000, F_per_gpu=10_000),
     "C3": dict(P=45, n=5000, F=1_000, D_per_gpu=1_000, nmfp=True),
     "C4": dict(P=68, n=10_000, F_per_gpu=125_000),
+    "T": dict(P=3, n=300, F_per_gpu=256),  # tiny: contract tests only (tests/test_bench_contract.py)
 }
 M_BASIS = 72
 M_VAR = 60  # per-draw (red-noise) block of the basis: 30 Fourier components
