@@ -263,6 +263,28 @@ __global__ void __launch_bounds__(768, 1) warp_mix_kernel(int iters, double seed
   if (s == 12345.678) sink[0] = s;
 }
 
+// kind 16: legacy INT8 tensor MMA (mma.sync.m16n8k32.s8, int32 accumulation) from registers -- how far the
+// warp-level MMA path gets on its own; the split-precision plan of DESIGN.md section 8 needs ~36 such products
+// per fp64 product, so it pays only if this rate (or tcgen05's) is well above 36x the fp64 pipe.
+__global__ void __launch_bounds__(256) imma_peak_kernel(int iters, int seed, double* sink) {
+  int c[8][4];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = c[k][2] = c[k][3] = seed + k;
+  const unsigned a0 = 0x01020304u + threadIdx.x, a1 = 0x02030405u, a2 = 0x03040506u, a3 = 0x04050607u;
+  const unsigned b0 = 0x01010101u, b1 = 0x02020202u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+r"(c[k][0]), "+r"(c[k][1]), "+r"(c[k][2]), "+r"(c[k][3])
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1] + c[k][2] + c[k][3];
+  if (s == 123456789) sink[0] = (double)s;
+}
+
 int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
   int dev = 0, sms = 0;
   FFP_CUDA(cudaGetDevice(&dev));
@@ -305,6 +327,7 @@ int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
     else if (kind == 10) dmma_tile_kernel<9, 2><<<sms, 512>>>(iters, 1.0, sink);   // 4 warps / sub-partition
     else if (kind == 11) dmma_tile_kernel<9, 4><<<sms, 128>>>(iters, 1.0, sink);   // 1 warp / sub-partition
     else if (kind == 12) dmma_16816_kernel<<<sms, 256>>>(iters, 1.0, sink);
+    else if (kind == 16) imma_peak_kernel<<<grid, 256>>>(iters, 1, sink);
     else if (kind == 13) warp_mix_kernel<32><<<sms, 768>>>(iters, 1.0, sink);   // DFMA asks for 1/8 of DMMA's pipe time
     else if (kind == 14) warp_mix_kernel<50><<<sms, 768>>>(iters, 1.0, sink);   // ~0.195 (the sweep kernel's mix)
     else if (kind == 15) warp_mix_kernel<96><<<sms, 768>>>(iters, 1.0, sink);   // 3/8
@@ -325,6 +348,7 @@ int run_fp64_peak(int kind, int iters, double* tflops, double* ms_out) {
                            : kind == 10 ? (double)sms * 16 * 2 * 18 * 256.0 * iters
                            : kind == 11 ? (double)sms * 4 * 2 * 36 * 256.0 * iters
                            : kind == 12 ? (double)sms * 8 * 4 * 2048.0 * iters
+                           : kind == 16 ? (double)grid * 8 * 8.0 * (16.0 * 8 * 32) * iters
                            : kind >= 13 && kind <= 15
                                ? (double)sms * (8 * 8 * 256.0 * iters +
                                                 16 * 32 * 16.0 * (double)((long long)iters * 2 * (kind == 13 ? 32 : kind == 14 ? 50 : 96) / 256))

@@ -164,7 +164,8 @@ int fastfp_xcy_blockn(int device, int64_t n, int64_t m, const double* Nvec, cons
  * (kind 1), or both interleaved (kind 2), on the device and returns TFLOP/s; bench.py uses
  * kind 1 as the measured fp64-pipe denominator (MEASURED_PEAKS.json has no fp64 figure). Kinds 3-12
  * are the kernel-design probes of csrc/microbench.cu; 13-15 run the sweep kernel's warp
- * specialisation (8 DMMA warps + 16 DFMA warps) on registers only. */
+ * specialisation (8 DMMA warps + 16 DFMA warps) on registers only; 16 = legacy INT8 mma.sync rate
+ * (reported as 2 x MAC/s in the same unit). */
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms);
 
 #ifdef __cplusplus
