@@ -1,0 +1,95 @@
+// Producer-side cost probe for the round-2 plan: per (TOA, frequency) pair the fp64
+// sincos of the sweep kernel, the five weighted sums, and the error-free split of sin and cos into 8 signed
+// 7-bit digits each (16 bytes, stored to shared memory). Digits by the round-to-nearest magic-constant trick:
+// the leading five in fp64 (three operations each), the last three in fp32 once the remainder fits 24 bits.
+// Prints pairs per SM per cycle, to set against the MMA time of the 36 INT8 products.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../fastfp_b200/csrc -o slice_rate_probe slice_rate_probe.cu
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include "ffp_sincos.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
+
+// x in [-1, 1] -> 8 digits of x/2 (|.| <= 1/2), d_i in [-64, 64], x/2 = sum d_i 2^(-7 i) (+ remainder < 2^-57)
+__device__ __forceinline__ uint2 split8(double x) {
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: low mantissa word of (v + MAGIC) is rint(v) in two's complement
+  double r = x * 0.5;
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int i = 1; i <= 5; ++i) {
+    const double w = (double)(1ull << (7 * i));
+    const double t = fma(r, w, MAGIC);
+    const double d = t - MAGIC;
+    r = fma(-d, 1.0 / w, r);
+    const uint32_t b = (uint32_t)__double2loint(t) & 0xffu;
+    if (i <= 4) lo |= b << (8 * (i - 1)); else hi |= b;
+  }
+  // |r| <= 2^-36: r * 2^56 is an integer below 2^21 in magnitude -> exact in fp32
+  float rf = (float)(r * 72057594037927936.0);  // 2^56
+  const float MAGICF = 12582912.0f;             // 1.5 * 2^23
+#pragma unroll
+  for (int i = 6; i <= 8; ++i) {
+    const float w = 1.0f / (float)(1u << (7 * (8 - i)));  // digit i has weight 2^(7 (8 - i)) in rf
+    const float t = fmaf(rf, w, MAGICF);
+    const float d = t - MAGICF;
+    rf = fmaf(-d, 1.0f / w, rf);
+    hi |= ((uint32_t)__float_as_int(t) & 0xffu) << (8 * (i - 5));
+  }
+  return make_uint2(lo, hi);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) slice_kernel(int iters, double om0, double* sink) {
+  __shared__ uint4 tile[256];
+  const double t = 4.6e9 + 1000.0 * threadIdx.x + 7.0 * blockIdx.x, ninv = 1e13, wv = 0.3;
+  double s2[5] = {0, 0, 0, 0, 0};
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {  // four independent pairs per iteration, as a producer thread owns per chunk
+      const double om = om0 * (1.0 + 1e-3 * (4 * it + e));
+      double s, c;
+      ffp::sincos_cw(__dmul_rn(om, t), &s, &c);
+      const double sn = s * ninv, cn = c * ninv;
+      s2[0] = fma(sn, s, s2[0]); s2[1] = fma(sn, c, s2[1]); s2[2] = fma(cn, c, s2[2]);
+      s2[3] = fma(s, wv, s2[3]); s2[4] = fma(c, wv, s2[4]);
+      if (SPLIT) {
+        const uint2 ds = split8(s), dc = split8(c);
+        tile[(threadIdx.x + e) & 255] = make_uint4(ds.x, ds.y, dc.x, dc.y);
+      } else {
+        tile[(threadIdx.x + e) & 255] = make_uint4(__double2loint(s), __double2hiint(s), __double2loint(c), __double2hiint(c));
+      }
+    }
+    acc ^= tile[(threadIdx.x * 7 + it) & 255].x;
+  }
+  if (s2[0] + s2[1] + s2[2] + s2[3] + s2[4] == 1.2345 || acc == 0x12345678u) sink[0] = s2[0];
+}
+
+int main(int argc, char** argv) {
+  const int iters = argc > 1 ? atoi(argv[1]) : 4000;
+  int dev = 0, sms = 0, khz = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+  double* sink; CK(cudaMalloc(&sink, 8));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int variant = 0; variant < 2; ++variant) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      CK(cudaEventRecord(e0));
+      if (variant) slice_kernel<true><<<sms * 4, 256>>>(iters, 6.283185307179586 * 1e-8, sink);
+      else slice_kernel<false><<<sms * 4, 256>>>(iters, 6.283185307179586 * 1e-8, sink);
+      CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep && ms < best) best = ms;
+    }
+    const double pairs = (double)sms * 4 * 256 * iters * 4.0;
+    const double cyc = best * 1e-3 * khz * 1e3;
+    printf("%s: %.3f ms, %.3f pairs per SM per cycle at %d MHz -> %.0f cycles per 2048-pair chunk\n",
+           variant ? "sincos + sums + split into 2x8 digits" : "sincos + sums only                    ", best,
+           pairs / sms / cyc, khz / 1000, 2048.0 / (pairs / sms / cyc));
+  }
+  return 0;
+}
