@@ -40,7 +40,26 @@ __device__ __forceinline__ uint2 split8(double x) {
   return make_uint2(lo, hi);
 }
 
-template <bool SPLIT>
+// Variant: UNSIGNED digits (tcgen05 kind::i8 takes unsigned 8-bit operands too). y = x/2 + 1/2 in [0, 1] as a
+// 56-bit fixed-point number q; its base-128 digits are plain bit fields -- no carries, no per-digit floating-point
+// work: two magic-constant roundings give the high and low 28 bits, integer shifts/masks do the rest. The offset is
+// removed after the MMAs (it contributes (1/2) * rowsum(G), known per row). The top digit may be 128 (x = 1).
+__device__ __forceinline__ uint32_t spread28(uint32_t v) {  // 4 x 7-bit fields -> 4 bytes, most significant digit in byte 0
+  return ((v >> 21) & 0xffu) | (((v >> 14) & 0x7fu) << 8) | (((v >> 7) & 0x7fu) << 16) | ((v & 0x7fu) << 24);
+}
+__device__ __forceinline__ uint2 split8u(double x) {
+  const double MAGIC = 6755399441055744.0;
+  const double t1 = fma(x, 134217728.0, MAGIC);                 // rint(x 2^27), |.| <= 2^27
+  const double rem = fma(-(t1 - MAGIC), 1.0 / 134217728.0, x);  // exact, in [-2^-28, 2^-28]
+  const double t2 = fma(rem, 36028797018963968.0, MAGIC);       // rint(rem 2^55), |.| <= 2^27
+  const int lo = __double2loint(t2);
+  // q = (x/2 + 1/2) 2^56 = (hi_s + 2^27) 2^28 + lo_s: the offset is added in integers (forming x/2 + 1/2 in fp64
+  // would round away the low bits of x); borrow when the low part is negative
+  const uint32_t hi = (uint32_t)(__double2loint(t1) + (1 << 27) + (lo >> 31));
+  return make_uint2(spread28(hi), spread28((uint32_t)lo & 0x0fffffffu));
+}
+
+template <int SPLIT>
 __global__ void __launch_bounds__(256) slice_kernel(int iters, double om0, double* sink) {
   __shared__ uint4 tile[256];
   const double t = 4.6e9 + 1000.0 * threadIdx.x + 7.0 * blockIdx.x, ninv = 1e13, wv = 0.3;
@@ -55,8 +74,11 @@ __global__ void __launch_bounds__(256) slice_kernel(int iters, double om0, doubl
       const double sn = s * ninv, cn = c * ninv;
       s2[0] = fma(sn, s, s2[0]); s2[1] = fma(sn, c, s2[1]); s2[2] = fma(cn, c, s2[2]);
       s2[3] = fma(s, wv, s2[3]); s2[4] = fma(c, wv, s2[4]);
-      if (SPLIT) {
+      if (SPLIT == 1) {
         const uint2 ds = split8(s), dc = split8(c);
+        tile[(threadIdx.x + e) & 255] = make_uint4(ds.x, ds.y, dc.x, dc.y);
+      } else if (SPLIT == 2) {
+        const uint2 ds = split8u(s), dc = split8u(c);
         tile[(threadIdx.x + e) & 255] = make_uint4(ds.x, ds.y, dc.x, dc.y);
       } else {
         tile[(threadIdx.x + e) & 255] = make_uint4(__double2loint(s), __double2hiint(s), __double2loint(c), __double2hiint(c));
@@ -75,12 +97,13 @@ int main(int argc, char** argv) {
   CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
   double* sink; CK(cudaMalloc(&sink, 8));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  for (int variant = 0; variant < 2; ++variant) {
+  for (int variant = 0; variant < 3; ++variant) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
       CK(cudaEventRecord(e0));
-      if (variant) slice_kernel<true><<<sms * 4, 256>>>(iters, 6.283185307179586 * 1e-8, sink);
-      else slice_kernel<false><<<sms * 4, 256>>>(iters, 6.283185307179586 * 1e-8, sink);
+      if (variant == 1) slice_kernel<1><<<sms * 4, 256>>>(iters, 6.283185307179586 * 1e-8, sink);
+      else if (variant == 2) slice_kernel<2><<<sms * 4, 256>>>(iters, 6.283185307179586 * 1e-8, sink);
+      else slice_kernel<0><<<sms * 4, 256>>>(iters, 6.283185307179586 * 1e-8, sink);
       CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
       float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
       if (rep && ms < best) best = ms;
@@ -88,7 +111,7 @@ int main(int argc, char** argv) {
     const double pairs = (double)sms * 4 * 256 * iters * 4.0;
     const double cyc = best * 1e-3 * khz * 1e3;
     printf("%s: %.3f ms, %.3f pairs per SM per cycle at %d MHz -> %.0f cycles per 2048-pair chunk\n",
-           variant ? "sincos + sums + split into 2x8 digits" : "sincos + sums only                    ", best,
+           variant == 1 ? "sincos + sums + 2x8 signed digits  " : variant == 2 ? "sincos + sums + 2x8 unsigned digits" : "sincos + sums only                 ", best,
            pairs / sms / cyc, khz / 1000, 2048.0 / (pairs / sms / cyc));
   }
   return 0;
