@@ -26,7 +26,8 @@ __host__ __device__ inline int sw128(int r, int c) { return (r >> 3) * 1024 + (r
 
 __global__ void __launch_bounds__(128, 1) split_kernel(const int8_t* __restrict__ Ap, const int8_t* __restrict__ Bp, int K,
                                                         const double* __restrict__ row_scale, double* __restrict__ Y,
-                                                        int* __restrict__ status) {
+                                                        int* __restrict__ status, int b_unsigned,
+                                                        const double* __restrict__ row_offset) {
   extern __shared__ unsigned char raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                    // [NS][128 rows x 128 B], swizzled
@@ -50,7 +51,9 @@ __global__ void __launch_bounds__(128, 1) split_kernel(const int8_t* __restrict_
     return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
   };
-  const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  // B format bit: 1 = signed 8-bit, 0 = unsigned 8-bit (the digits of S/2 + 1/2)
+  const uint32_t idesc = (2u << 4) | (1u << 7) | ((b_unsigned ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+                         ((uint32_t)(M >> 4) << 24);
   const int nkb = K / KB;
   int ok_all = 1;
   for (int kb = 0; kb < nkb; ++kb) {
@@ -115,11 +118,17 @@ __global__ void __launch_bounds__(128, 1) split_kernel(const int8_t* __restrict_
       for (int q = 0; q < 8; ++q) y[q] = fma((double)(int)v[q], wgt, y[q]);
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) Y[(size_t)row * N + c0 + q] = y[q] * rs;
+    for (int q = 0; q < 8; ++q) Y[(size_t)row * N + c0 + q] = (y[q] - row_offset[row]) * rs;  // offset: (1/2) sum_k g_k
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "n"(512));
+}
+
+static void digits_unsigned(long double y, int* d) {  // y in [0, 1] -> 8 base-128 digits (the first may be 128)
+  long double q = floorl(y * ldexpl(1.0L, 56) + 0.5L);
+  for (int i = NS - 1; i >= 1; --i) { const long double hi = floorl(q / 128.0L); d[i] = (int)(q - hi * 128.0L); q = hi; }
+  d[0] = (int)q;
 }
 
 static void digits(long double x, int* d) {  // |x| <= 1/2 -> 8 signed 7-bit digits, x ~ sum d_i 2^(-7 (i + 1))
@@ -134,11 +143,12 @@ static void digits(long double x, int* d) {  // |x| <= 1/2 -> 8 signed 7-bit dig
 
 int main(int argc, char** argv) {
   const int K = argc > 1 ? atoi(argv[1]) : 1024;
+  const int b_unsigned = argc > 2 ? atoi(argv[2]) : 0;
   if (K % KB) { printf("K must be a multiple of %d\n", KB); return 1; }
   std::mt19937_64 rng(7);
   std::normal_distribution<double> nd(0.0, 1.0);
   std::uniform_real_distribution<double> ud(-1.0, 1.0), us(-2.0, 2.0);
-  std::vector<double> G((size_t)M * K), S((size_t)N * K), rs(M);
+  std::vector<double> G((size_t)M * K), S((size_t)N * K), rs(M), roff(M, 0.0);
   std::vector<int8_t> Ap((size_t)NS * M * K), Bp((size_t)NS * N * K);
   for (int m = 0; m < M; ++m) {
     const double sc = pow(10.0, us(rng));
@@ -151,22 +161,30 @@ int main(int argc, char** argv) {
       digits(ldexpl((long double)G[(size_t)m * K + k], -e), d);
       for (int i = 0; i < NS; ++i) Ap[((size_t)i * M + m) * K + k] = (int8_t)d[i];
     }
+    if (b_unsigned) {  // (1/2) sum_k g_k with g = G / 2^e: what the +1/2 offset of every S entry adds to this row
+      long double acc = 0;
+      for (int k = 0; k < K; ++k) acc += ldexpl((long double)G[(size_t)m * K + k], -e);
+      roff[m] = (double)(0.5L * acc);
+    }
   }
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
       S[(size_t)n * K + k] = ud(rng);
       int d[NS];
-      digits((long double)S[(size_t)n * K + k] * 0.5L, d);
-      for (int i = 0; i < NS; ++i) Bp[((size_t)i * N + n) * K + k] = (int8_t)d[i];
+      if (b_unsigned) digits_unsigned((long double)S[(size_t)n * K + k] * 0.5L + 0.5L, d);
+      else digits((long double)S[(size_t)n * K + k] * 0.5L, d);
+      for (int i = 0; i < NS; ++i) Bp[((size_t)i * N + n) * K + k] = (int8_t)(uint8_t)d[i];
     }
-  int8_t *dA, *dB; double *dR, *dY; int* dS;
+  int8_t *dA, *dB; double *dR, *dY, *dO; int* dS;
+  CK(cudaMalloc(&dO, M * 8));
+  CK(cudaMemcpy(dO, roff.data(), M * 8, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&dA, Ap.size())); CK(cudaMalloc(&dB, Bp.size())); CK(cudaMalloc(&dR, M * 8)); CK(cudaMalloc(&dY, (size_t)M * N * 8));
   CK(cudaMalloc(&dS, 4));
   CK(cudaMemcpy(dA, Ap.data(), Ap.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, Bp.data(), Bp.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dR, rs.data(), M * 8, cudaMemcpyHostToDevice));
   const size_t sm = (size_t)NS * (A_PLANE + B_PLANE) + 1024;
   CK(cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  split_kernel<<<1, 128, sm>>>(dA, dB, K, dR, dY, dS);
+  split_kernel<<<1, 128, sm>>>(dA, dB, K, dR, dY, dS, b_unsigned, dO);
   CK(cudaDeviceSynchronize());
   std::vector<double> Y((size_t)M * N);
   int st = 0;
@@ -183,7 +201,7 @@ int main(int argc, char** argv) {
       const double e64 = (double)(fabsl((long double)p64 - t) / sc) / 2.220446049250313e-16;
       worst = fmax(worst, e); worst64 = fmax(worst64, e64); sum += e;
     }
-  printf("K=%d, 36 INT8 products per block, barriers completed=%d: split product max err %.3f mean %.3f, plain fp64 fma chain max err %.3f "
-         "[eps * sum|G||S|]\n", K, st, worst, sum / (M * N), worst64);
+  printf("K=%d, B digits %s, 36 INT8 products per block, barriers completed=%d: split product max err %.3f mean %.3f, plain fp64 fma chain max err %.3f "
+         "[eps * sum|G||S|]\n", K, b_unsigned ? "unsigned (offset 1/2)" : "signed", st, worst, sum / (M * N), worst64);
   return worst < 4.0 ? 0 : 2;
 }
