@@ -15,19 +15,23 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
 
-constexpr int M = 128, N = 64, NS = 8, KB = 128;  // rows, columns, digit planes, K bytes per staged block
-constexpr int A_PLANE = M * KB, B_PLANE = N * KB;
+constexpr int M = 128, N = 64, NS = 8;  // rows, columns, digit planes; KB = K bytes per staged block (128, 64 or 32)
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// byte offset of (row r, K byte c) inside one K-major SWIZZLE_128B tile: 8-row groups of 1024 bytes, the
-// 16-byte chunk index XORed with the row inside the group
-__host__ __device__ inline int sw128(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + (((c >> 4) ^ (r & 7)) << 4) + (c & 15); }
+// byte offset of (row r, K byte c) inside one K-major swizzled tile whose rows are KB bytes long (SWIZZLE_128B /
+// 64B / 32B for KB = 128 / 64 / 32): 8-row groups of 8 KB bytes, the 16-byte chunk index XORed with the low row bits
+template <int KB>
+__host__ __device__ inline int swz(int r, int c) {
+  return (r >> 3) * (8 * KB) + (r & 7) * KB + (((c >> 4) ^ ((r & 7) >> (KB == 128 ? 0 : KB == 64 ? 1 : 2))) << 4) + (c & 15);
+}
 
+template <int KB>
 __global__ void __launch_bounds__(128, 1) split_kernel(const int8_t* __restrict__ Ap, const int8_t* __restrict__ Bp, int K,
                                                         const double* __restrict__ row_scale, double* __restrict__ Y,
                                                         int* __restrict__ status, int b_unsigned,
                                                         const double* __restrict__ row_offset) {
+  constexpr int A_PLANE = M * KB, B_PLANE = N * KB;
   extern __shared__ unsigned char raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                    // [NS][128 rows x 128 B], swizzled
@@ -47,9 +51,9 @@ __global__ void __launch_bounds__(128, 1) split_kernel(const int8_t* __restrict_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n");
   const uint32_t tm = tmem_base;
-  auto desc = [](uint32_t addr) {
-    return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
+  auto desc = [](uint32_t addr) {  // SBO = one 8-row group; layout type 2 / 4 / 6 = SWIZZLE_128B / 64B / 32B
+    return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)((8 * KB) >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)(KB == 128 ? 2 : KB == 64 ? 4 : 6) << 61);
   };
   // B format bit: 1 = signed 8-bit, 0 = unsigned 8-bit (the digits of S/2 + 1/2)
   const uint32_t idesc = (2u << 4) | (1u << 7) | ((b_unsigned ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
@@ -58,15 +62,15 @@ __global__ void __launch_bounds__(128, 1) split_kernel(const int8_t* __restrict_
   int ok_all = 1;
   for (int kb = 0; kb < nkb; ++kb) {
     // stage the digit planes of this K block: 16-byte chunks, swizzled
-    for (int u = tid; u < NS * M * 8; u += 128) {
-      const int p = u / (M * 8), r = (u / 8) % M, ch = u % 8;
+    for (int u = tid; u < NS * M * (KB / 16); u += 128) {
+      const int p = u / (M * (KB / 16)), r = (u / (KB / 16)) % M, ch = u % (KB / 16);
       const uint4 v = *reinterpret_cast<const uint4*>(Ap + ((size_t)(p * M + r) * K + (size_t)kb * KB + ch * 16));
-      *reinterpret_cast<uint4*>(sA + p * A_PLANE + sw128(r, ch * 16)) = v;
+      *reinterpret_cast<uint4*>(sA + p * A_PLANE + swz<KB>(r, ch * 16)) = v;
     }
-    for (int u = tid; u < NS * N * 8; u += 128) {
-      const int p = u / (N * 8), r = (u / 8) % N, ch = u % 8;
+    for (int u = tid; u < NS * N * (KB / 16); u += 128) {
+      const int p = u / (N * (KB / 16)), r = (u / (KB / 16)) % N, ch = u % (KB / 16);
       const uint4 v = *reinterpret_cast<const uint4*>(Bp + ((size_t)(p * N + r) * K + (size_t)kb * KB + ch * 16));
-      *reinterpret_cast<uint4*>(sB + p * B_PLANE + sw128(r, ch * 16)) = v;
+      *reinterpret_cast<uint4*>(sB + p * B_PLANE + swz<KB>(r, ch * 16)) = v;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n");
@@ -144,7 +148,8 @@ static void digits(long double x, int* d) {  // |x| <= 1/2 -> 8 signed 7-bit dig
 int main(int argc, char** argv) {
   const int K = argc > 1 ? atoi(argv[1]) : 1024;
   const int b_unsigned = argc > 2 ? atoi(argv[2]) : 0;
-  if (K % KB) { printf("K must be a multiple of %d\n", KB); return 1; }
+  const int KBr = argc > 3 ? atoi(argv[3]) : 128;  // K bytes per staged block = swizzle width: 128, 64 or 32
+  if ((KBr != 128 && KBr != 64 && KBr != 32) || K % KBr) { printf("usage: K (multiple of the stage) [unsigned 0|1] [stage 128|64|32]\n"); return 1; }
   std::mt19937_64 rng(7);
   std::normal_distribution<double> nd(0.0, 1.0);
   std::uniform_real_distribution<double> ud(-1.0, 1.0), us(-2.0, 2.0);
@@ -182,9 +187,17 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dS, 4));
   CK(cudaMemcpy(dA, Ap.data(), Ap.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, Bp.data(), Bp.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dR, rs.data(), M * 8, cudaMemcpyHostToDevice));
-  const size_t sm = (size_t)NS * (A_PLANE + B_PLANE) + 1024;
-  CK(cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  split_kernel<<<1, 128, sm>>>(dA, dB, K, dR, dY, dS, b_unsigned, dO);
+  const size_t sm = (size_t)NS * (M + N) * KBr + 1024;
+  if (KBr == 128) {
+    CK(cudaFuncSetAttribute(split_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    split_kernel<128><<<1, 128, sm>>>(dA, dB, K, dR, dY, dS, b_unsigned, dO);
+  } else if (KBr == 64) {
+    CK(cudaFuncSetAttribute(split_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    split_kernel<64><<<1, 128, sm>>>(dA, dB, K, dR, dY, dS, b_unsigned, dO);
+  } else {
+    CK(cudaFuncSetAttribute(split_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    split_kernel<32><<<1, 128, sm>>>(dA, dB, K, dR, dY, dS, b_unsigned, dO);
+  }
   CK(cudaDeviceSynchronize());
   std::vector<double> Y((size_t)M * N);
   int st = 0;
@@ -201,7 +214,7 @@ int main(int argc, char** argv) {
       const double e64 = (double)(fabsl((long double)p64 - t) / sc) / 2.220446049250313e-16;
       worst = fmax(worst, e); worst64 = fmax(worst64, e64); sum += e;
     }
-  printf("K=%d, B digits %s, 36 INT8 products per block, barriers completed=%d: split product max err %.3f mean %.3f, plain fp64 fma chain max err %.3f "
-         "[eps * sum|G||S|]\n", K, b_unsigned ? "unsigned (offset 1/2)" : "signed", st, worst, sum / (M * N), worst64);
+  printf("K=%d, stage/swizzle %d B, B digits %s, 36 INT8 products per block, barriers completed=%d: split product max err %.3f mean %.3f, plain fp64 fma chain max err %.3f "
+         "[eps * sum|G||S|]\n", K, KBr, b_unsigned ? "unsigned (offset 1/2)" : "signed", st, worst, sum / (M * N), worst64);
   return worst < 4.0 ? 0 : 2;
 }
