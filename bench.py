@@ -1,28 +1,37 @@
 #!/usr/bin/env python
 """Benchmark of the Fp frequency-sweep hot path (BASELINE.json metric: Fp evals/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C4]  (T = tiny, contract tests only) [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C2|C3|C5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one sweep of the plain-Fp statistic over the rank's frequency shard for all pulsars
-(`FastFp.calculate_Fp` with an array of frequencies -> one persistent CUDA kernel + the ordered
-pulsar sum), followed for N > 1 by the single NCCL all-gather of the per-bin values.
+Default workload = the configuration the metric is quoted on (BASELINE.json north_star / configs[3]):
 
-Workload (synthetic; seeds in fastfp_b200/synth.py):
-  C2 (default)  45 pulsars x 5000 TOAs, m = 72, 10 000 frequencies PER GPU   (BASELINE configs[1])
-  C4            68 pulsars x 10 000 TOAs, m = 72, 125 000 frequencies PER GPU (= configs[3], the
-                1e6-frequency sweep, when run on 8 GPUs)
-  C3            noise-marginalised Fp (NMFP): 45 pulsars x 5000 TOAs, 1000 frequencies x 1000 noise
-                draws PER GPU (BASELINE configs[2]); the draw axis is sharded across ranks
-For C2/C4 the frequency axis is sharded across ranks (weak scaling: per-GPU work is fixed), pulsar arrays
-are replicated; `value` is whole-job evals/s = (all frequencies x pulsars) / max-over-ranks time.
+  C4 (default)  Fp sweep, 68 pulsars x 10 000 TOAs, m = 72, F = 1 000 000 frequencies IN TOTAL, sharded over
+                the N ranks (STRONG scaling: N = 1 sweeps all 1e6 bins on one GPU), one NCCL all-gather of
+                the per-bin values at the end.
+  C2            Fp sweep, 45 x 5000, m = 72, 10 000 frequencies PER GPU (configs[1]; weak scaling)
+  C3            noise-marginalised Fp, 45 x 5000, 1000 frequencies x 1000 draws PER GPU (configs[2]; the
+                draw axis is sharded; weak scaling)
+  C5            noise-marginalised Fp with a block-diagonal (kernel-ECORR) N: 68 x 10 000 TOAs in 2500
+                epochs of 4, 10 000 frequencies x 10 000 draws IN TOTAL, draws sharded (configs[4]; strong)
+  T             tiny, contract tests only
 
-Timing: W >= 3 untimed warm-up steps after a clock spin-up, then exactly K steps, each bracketed
-by CUDA events on the launching stream, with an L2 flush (write of a 256 MiB buffer) between
-steps outside the timed brackets; barrier + synchronize on both sides; max over ranks.
-`--impl reference` times the CPU restatement of the reference (oracle/, NumPy + threaded BLAS,
-all host cores) on a bounded sample of the same workload; it is the one place outside tests/ and
-smoke() that executes oracle/.
+One "step" = one pass of the hot path over the rank's shard through the public API (`FastFp.calculate_Fp`
+/ `NMFP.calculate_nmfp`) followed for N > 1 by the single NCCL all-gather. With the default workload the
+JSON line also carries `secondary.C2` and `secondary.C3` (same fields, a few steps each) unless
+`--no-secondary` is given.
+
+Timing: a clock spin-up, W >= 3 untimed warm-up steps, then exactly K steps, each bracketed by CUDA events
+on the launching stream with an L2 flush (a 256 MiB buffer written) between steps outside the brackets;
+barrier + synchronize on both sides; max over ranks. `e2e` repeats the measurement through the same public
+call with HOST buffers (pinned): host->device copy of the step's inputs and device->host copy of the result
+inside the timed region, including the host-side content hash that guards the cached device pack.
+
+Checks recorded in the line (`checks`): (1) the NCCL-gathered output equals what a single GPU computes for
+the same bins, bit for bit (every rank recomputes a slice of ANOTHER rank's shard); (2) an untimed oracle
+spot check of bins of the timed result. `--impl reference` times the CPU restatement of the reference
+(oracle/, NumPy + threaded pieces, all host cores) on a bounded sample of the same workload; together with
+`cpu_baseline` and the spot check it is the only place outside tests/ and smoke() that executes oracle/.
 """
 from __future__ import annotations
 
@@ -41,13 +50,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "C2": dict(P=45, n=5000, F_per_gpu=10_000),
-    "C3": dict(P=45, n=5000, F=1_000, D_per_gpu=1_000, nmfp=True),
-    "C4": dict(P=68, n=10_000, F_per_gpu=125_000),
-    "T": dict(P=3, n=300, F_per_gpu=256),  # tiny: contract tests only (tests/test_bench_contract.py)
+    "C4": dict(kind="fp", P=68, n=10_000, F_total=1_000_000, scaling="strong"),
+    "C2": dict(kind="fp", P=45, n=5000, F_per_gpu=10_000, scaling="weak"),
+    "C3": dict(kind="nmfp", P=45, n=5000, F=1_000, D_per_gpu=1_000, scaling="weak"),
+    "C5": dict(kind="nmfp", P=68, n=10_000, F=10_000, D_total=10_000, blockn=True, epoch=4, scaling="strong"),
+    "T": dict(kind="fp", P=3, n=300, F_per_gpu=256, scaling="weak"),  # tiny: tests/test_bench_contract.py
+    "TN": dict(kind="nmfp", P=3, n=300, F=64, D_per_gpu=16, scaling="weak"),
 }
 M_BASIS = 72
 M_VAR = 60  # per-draw (red-noise) block of the basis: 30 Fourier components
+METRIC = "Fp evals/sec (freqs x pulsars x draws)"
+
+
+def total_F(wl, world):
+    return wl["F_total"] if "F_total" in wl else wl["F_per_gpu"] * world
+
+
+def total_D(wl, world):
+    return wl["D_total"] if "D_total" in wl else wl["D_per_gpu"] * world
 
 
 def bytes_per_eval(n, m):
@@ -70,15 +90,17 @@ def nmfp_flops_per_eval(n, m, mv, F, D):
 
 
 def measured_traffic(workload):
-    """DRAM bytes of one sweep launch of this workload, from the committed ncu capture
-    (profiles/r1_dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum)."""
-    path = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-    try:
-        with open(path) as f:
-            d = json.load(f)[workload]
-        return float(d["dram_bytes_per_launch"]), "profiles/r1_dram_traffic.json (ncu, per launch of one GPU's shard)"
-    except (OSError, KeyError, ValueError):
-        return None, None
+    """DRAM bytes of one launch of the dominant kernel of this workload, from the committed ncu captures
+    (profiles/r*_dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); newest round first."""
+    for name in ("r2_dram_traffic.json", "r1_dram_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)[workload]
+            return float(d["dram_bytes_per_launch"]), f"profiles/{name} (ncu --set full, per launch, one GPU's shard: " \
+                                                      f"{d.get('shard', 'see file')})"
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, None
 
 
 def measured_peaks():
@@ -88,6 +110,24 @@ def measured_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_of(key, wl, gpus):
+    """The workload-defining part of the line: identical for `--impl ours` and `--impl reference`."""
+    if wl["kind"] == "nmfp":
+        D = total_D(wl, gpus)
+        ec = f" in {wl['n'] // wl['epoch']} epochs of {wl['epoch']} TOAs (block-diagonal kernel-ECORR N)" if wl.get("blockn") else ""
+        per = "in total, draws sharded" if "D_total" in wl else f"= {wl['D_per_gpu']} per GPU"
+        name = (f"{key}: noise-marginalised Fp, {wl['P']} pulsars x {wl['n']} TOAs{ec}, m={M_BASIS} (12 timing-model + "
+                f"60 red-noise/CURN Fourier), {wl['F']} frequencies x {D} noise draws {per}, {gpus} GPU(s), fp64")
+        return {"workload": name, "P": wl["P"], "n_toas": wl["n"], "m": M_BASIS, "F": wl["F"], "D": D,
+                "n_gpus": gpus, "scaling": wl["scaling"]}
+    F = total_F(wl, gpus)
+    per = "in total, sharded over the GPUs" if "F_total" in wl else f"= {wl['F_per_gpu']} per GPU"
+    name = (f"{key}: Fp sweep, {wl['P']} pulsars x {wl['n']} TOAs, m={M_BASIS} (12 timing-model + 60 Fourier), "
+            f"{F} frequencies {per}, {gpus} GPU(s), red+white Woodbury C, fp64")
+    return {"workload": name, "P": wl["P"], "n_toas": wl["n"], "m": M_BASIS, "F": F, "D": 1, "n_gpus": gpus,
+            "scaling": wl["scaling"]}
 
 
 class ClockSampler:
@@ -119,43 +159,47 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm, smax, reasons = [], [], set()
+        sm, smax, pw, reasons = [], [], [], set()
         for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
             try:
                 sm.append(float(parts[0])); smax.append(float(parts[1]))
+                pw.append(float(parts[2]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
                 if val == "Active":
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(wl, steps=1, warmup=0, target_s=12.0):
-    """The reference's CPU path (oracle port: the vmapped program's formulas, batched over
-    frequency, spread over all host cores) on a bounded sample of the workload. The sample (all
-    pulsars of the workload x a calibrated number of frequencies) is sized for ~target_s seconds
-    per step. Returns evals/s and metadata."""
+# ---------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port) -- cpu_baseline and --impl reference
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_rate(wl, world=1, steps=1, warmup=0, target_s=12.0):
+    """Plain Fp: the vmapped program's formulas, batched over frequency, spread over all host cores, on a
+    bounded sample of the workload (all pulsars x a calibrated number of the grid's frequencies, spread
+    evenly over the grid) sized for ~target_s seconds per step. Returns evals/s and metadata."""
     from fastfp_b200 import synth
     from oracle import fp_oracle
 
     cores = os.cpu_count() or 1
     pta = synth.make_pta(wl["P"], wl["n"])
-    grid = synth.fp_freqs(wl["F_per_gpu"])
+    F_all = total_F(wl, world)
+    grid = synth.fp_freqs(F_all)
     common = (pta.toas, pta.residuals, pta.Nvecs, pta.Ts, pta.sigmas)
     chunk = 64
-    fcal = max(chunk, chunk * (-(-cores // wl["P"])))  # enough pieces to occupy every core
+    fcal = min(F_all, max(chunk, chunk * (-(-cores // wl["P"]))))  # enough pieces to occupy every core
     fp_oracle.fp_sweep_mt(grid[:fcal], *common, workers=cores, chunk=chunk)  # warm-up
     t0 = time.perf_counter()
     fp_oracle.fp_sweep_mt(grid[:fcal], *common, workers=cores, chunk=chunk)
     t_cal = time.perf_counter() - t0
-    Fs = int(min(wl["F_per_gpu"], max(fcal, fcal * target_s / max(t_cal, 1e-3))))
-    Fs = max(chunk, Fs // chunk * chunk)
-    freqs = grid[:: max(1, wl["F_per_gpu"] // Fs)][:Fs]
+    Fs = int(min(F_all, max(fcal, fcal * target_s / max(t_cal, 1e-3))))
+    Fs = max(min(chunk, F_all), Fs // chunk * chunk)
+    freqs = grid[:: max(1, F_all // Fs)][:Fs]
     for _ in range(warmup):
         fp_oracle.fp_sweep_mt(freqs, *common, workers=cores, chunk=chunk)
     times = []
@@ -166,32 +210,49 @@ def cpu_reference_rate(wl, steps=1, warmup=0, target_s=12.0):
     evals = wl["P"] * len(freqs)
     return evals / statistics.median(times), {
         "cores": cores, "kind": "port",
-        "sample": f"{wl['P']} pulsars x {wl['n']} TOAs x {len(freqs)} of the {wl['F_per_gpu']} frequencies "
-                  f"({evals} evals per step, median of {max(1, steps)} step(s)); NumPy/SciPy restatement of the "
+        "sample": f"{wl['P']} pulsars x {wl['n']} TOAs x {len(freqs)} of the {F_all} frequencies, evenly spaced over "
+                  f"the grid ({evals} evals per step, median of {max(1, steps)} step(s)); NumPy/SciPy restatement of the "
                   f"reference formulas, (pulsar, 64-frequency) pieces on a {cores}-thread pool, 1 BLAS thread each",
         "ms_per_step": statistics.median(times) * 1e3,
     }
 
 
 def nmfp_problem(wl):
-    from fastfp_b200 import CURN_container, RN_container, synth
+    """Inputs of an nmfp workload: (pta, containers, Nvecs-or-BlockNvecs, TNTs)."""
+    from fastfp_b200 import BlockNvec, CURN_container, RN_container, synth
 
     pta = synth.make_pta(wl["P"], wl["n"])
     curn = CURN_container(pta.Ffreqs)
     sigs = [RN_container(q, Ffreqs=pta.Ffreqs, add_curn=True, curn_container=curn) for q in pta.psrs]
-    return pta, sigs
+    if not wl.get("blockn"):
+        return pta, sigs, pta.Nvecs, pta.TNTs
+    # kernel ECORR: epochs of `epoch` consecutive TOAs, j_e ~ (0.3 .. 3) x 1e-13 s^2 (seeded)
+    rng = np.random.default_rng(20240607 + 777)
+    ep = wl["epoch"]
+    Nblk, TNTs = [], []
+    for p in range(wl["P"]):
+        n = wl["n"]
+        slices = [slice(a, a + ep) for a in range(0, n - ep + 1, ep)]
+        B = BlockNvec(pta.Nvecs[p], slices, rng.uniform(0.3, 3.0, len(slices)) * 1e-13)
+        TNT = pta.Ts[p].T @ B.solve(pta.Ts[p])
+        Nblk.append(B)
+        TNTs.append(0.5 * (TNT + TNT.T))
+    return pta, sigs, Nblk, TNTs
 
 
-def cpu_reference_rate_nmfp(wl, steps=1, warmup=0, target_s=12.0):
-    """The reference's CPU path for nmfp (oracle port): per draw ``_get_sigmas`` and the frequency
-    sweep of calculate_Fp over all pulsars, on all host cores; sample = all frequencies x a
-    calibrated number of draws."""
+def cpu_reference_rate_nmfp(wl, world=1, steps=1, warmup=0, target_s=12.0):
+    """nmfp: per draw ``_get_sigmas`` and the frequency sweep of calculate_Fp over all pulsars, on all host
+    cores; sample = a calibrated number of draws x (all, or for large F an evenly spaced subset of) the
+    frequencies. A block-diagonal N has no reference implementation (fastfp/utils.py:29-31): the port then
+    runs the diagonal-N program on the same shapes (a LOWER bound on what a CPU implementation would cost)."""
     from fastfp_b200 import synth
     from oracle import fp_oracle
 
     cores = os.cpu_count() or 1
-    pta, _ = nmfp_problem(wl)
-    freqs = synth.nmfp_freqs(wl["F"], pta.Tspan)
+    pta = synth.make_pta(wl["P"], wl["n"])
+    F_all = wl["F"]
+    Fs = min(F_all, 1024)
+    freqs = synth.nmfp_freqs(F_all, pta.Tspan)[:: max(1, F_all // Fs)][:Fs]
     phi_args = [dict(psr_name=q.name, n_tm=ntm, Ffreqs=pta.Ffreqs, add_curn=True, curn_Ffreqs=pta.Ffreqs)
                 for q, ntm in zip(pta.psrs, pta.n_tm)]
     common = (pta.toas, pta.residuals, pta.Nvecs, pta.Ts)
@@ -202,12 +263,13 @@ def cpu_reference_rate_nmfp(wl, steps=1, warmup=0, target_s=12.0):
             sigmas = fp_oracle.get_sigmas(pars, pta.TNTs, phi_args)
             fp_oracle.fp_sweep_mt(freqs, *common, sigmas, workers=cores, chunk=64)
 
-    samples = synth.draw_samples(pta, 64)
+    D_all = total_D(wl, world)
+    samples = synth.draw_samples(pta, min(64, D_all))
     run(samples, 1)  # warm-up
     t0 = time.perf_counter()
     run(samples, 1)
     t1 = time.perf_counter() - t0
-    nd = int(max(1, min(64, wl["D_per_gpu"], target_s / max(t1, 1e-3))))
+    nd = int(max(1, min(64, D_all, target_s / max(t1, 1e-3))))
     for _ in range(warmup):
         run(samples, nd)
     times = []
@@ -215,67 +277,284 @@ def cpu_reference_rate_nmfp(wl, steps=1, warmup=0, target_s=12.0):
         t0 = time.perf_counter()
         run(samples, nd)
         times.append(time.perf_counter() - t0)
-    evals = wl["P"] * wl["F"] * nd
+    evals = wl["P"] * len(freqs) * nd
     return evals / statistics.median(times), {
         "cores": cores, "kind": "port",
-        "sample": f"{wl['P']} pulsars x {wl['n']} TOAs x all {wl['F']} frequencies x {nd} of the "
-                  f"{wl['D_per_gpu']} draws ({evals} evals per step, median of {max(1, steps)} step(s)); NumPy/SciPy "
+        "sample": f"{wl['P']} pulsars x {wl['n']} TOAs x {len(freqs)} of the {F_all} frequencies x {nd} of the "
+                  f"{D_all} draws ({evals} evals per step, median of {max(1, steps)} step(s)); NumPy/SciPy "
                   f"restatement of NMFP.calculate_nmfp (per draw: _get_sigmas, then the Fp sweep in (pulsar, "
-                  f"64-frequency) pieces on a {cores}-thread pool, 1 BLAS thread each)",
+                  f"64-frequency) pieces on a {cores}-thread pool, 1 BLAS thread each)"
+                  + ("; diagonal-N program on the same shapes (the reference has no block-diagonal N)" if wl.get("blockn") else ""),
         "ms_per_step": statistics.median(times) * 1e3,
     }
 
 
-def run_reference_nmfp(args, wl, rank, world):
+def run_reference(args, key, wl, rank, world):
     if rank != 0:
         return
-    rate, meta = cpu_reference_rate_nmfp(wl, steps=args.steps, warmup=min(args.warmup, 1),
-                                         target_s=min(12.0, 120.0 / max(1, args.steps + min(args.warmup, 1))))
-    line = {
-        "impl": "reference", "metric": "Fp evals/sec (freqs x pulsars x draws)", "value": rate, "unit": "evals/s",
+    fn = cpu_reference_rate_nmfp if wl["kind"] == "nmfp" else cpu_reference_rate
+    rate, meta = fn(wl, world=args.gpus, steps=args.steps, warmup=min(args.warmup, 1),
+                    target_s=min(12.0, 120.0 / max(1, args.steps + min(args.warmup, 1))))
+    emit({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": meta["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, wl, args.gpus), "parallelism": "cpu-host"},
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(key, wl, args.gpus),
+        "run": {"parallelism": "cpu-host, all cores", "note": "each step = the bounded sample in cpu_baseline.sample"},
         "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": meta["cores"], "kind": meta["kind"],
                          "sample": meta["sample"]},
         "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    emit(line)
+    })
 
 
-def run_nmfp(args, wl, rank, world, local):
-    """Workload C3: NMFP.calculate_nmfp over (draws x frequencies); draws sharded across ranks."""
-    import torch
-    import torch.distributed as dist
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+class Ctx:
+    """Per-process CUDA / NCCL context shared by the primary and the secondary workloads."""
 
+    def __init__(self, rank, world, local):
+        import torch
+        import torch.distributed as dist
+
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the Fp hot path has no CPU fallback)")
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local = rank, world, local
+        torch.cuda.set_device(local)
+        self.dev = torch.device("cuda", local)
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush_buf = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """sum over `steps` of the CUDA-event time of fn(), L2 flushed before each; max over ranks (ms)"""
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        for a, b in ev:
+            self.flush_buf.fill_(1.0)  # L2 flush, outside the timed bracket
+            a.record()
+            fn()
+            b.record()
+        self.barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok):
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def e2e_steps_for(steps, ms_step):
+    """the end-to-end leg repeats the K steps unless that alone would take more than ~30 s"""
+    if ms_step * steps <= 30_000.0:
+        return steps
+    return max(3, int(30_000.0 / ms_step))
+
+
+def spot_bins(F, Tspan, freqs):
+    """bins of the timed result that are checked against the oracle: the grid ends, two interior bins and
+    (when the grid reaches down there) the bins next to the first red-noise Fourier frequencies"""
+    idx = sorted({0, 1, F // 3, F // 2, F - 2, F - 1} & set(range(F)))
+    return np.array(idx, dtype=np.int64)
+
+
+def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
+    """Plain-Fp workload: frequency axis sharded across ranks, pulsar arrays replicated."""
     import fastfp_b200
     from fastfp_b200 import _cabi, parallel, synth
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the Fp hot path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=dev)
+    torch, rank, world, dev = ctx.torch, ctx.rank, ctx.world, ctx.dev
+    pta = synth.make_pta(wl["P"], wl["n"])
+    F_total = total_F(wl, world)
+    freqs_np = synth.fp_freqs(F_total)
+    freqs_host = torch.from_numpy(freqs_np).pin_memory()
+    fp = fastfp_b200.FastFp(pta.psrs, device=ctx.local)
+    mats = (pta.Nvecs, pta.Ts, pta.sigmas)
+    t0 = time.perf_counter()
+    pack = fp.prepare(*mats)
+    torch.cuda.synchronize()
+    pack_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    fp.prepare(*mats)  # steady state: the content hash of the three lists (every byte), no rebuild
+    hash_ms = (time.perf_counter() - t0) * 1e3
+    freqs_dev = freqs_host.to(dev)
+    lo, hi, per = parallel.shard_bounds(F_total, rank, world)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def step_device():
+        """inputs resident in HBM: sweep the shard, all-gather the bins"""
+        return parallel.sharded_sweep(lambda f: fp.calculate_Fp(f, *mats), freqs_dev)
+
+    out_pinned = torch.empty(F_total, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        """public API with host buffers: H2D of the shard's frequencies, sweep, gather, D2H of Fp"""
+        f = freqs_host[lo:hi].to(dev, non_blocking=True)
+        full = parallel.sharded_sweep(lambda _: fp.calculate_Fp(f, *mats), freqs_dev)
+        out_pinned.copy_(full, non_blocking=True)
+        return out_pinned
+
+    # clock spin-up (the SM clock needs ~0.4 s of load to leave its idle state), then W warm-ups. The
+    # spin-up is wall-clock bounded, so it must stay rank-local: no collective inside.
+    shard0 = freqs_dev[lo:min(hi, lo + 16384)].contiguous()
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.5:
+        fp.calculate_Fp(shard0, *mats)
         torch.cuda.synchronize()
+    ctx.barrier()
+    for _ in range(warmup):
+        step_device()
+    sampler = ClockSampler(ctx.local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _cabi.kernel_launches()
+    total_ms = ctx.timed(step_device, steps)
+    launches = _cabi.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = total_ms / steps
+    ne2e = e2e_steps_for(steps, ms_step)
+    for _ in range(2 if ms_step < 1000.0 else 1):
+        step_e2e()
+    e2e_ms = ctx.timed(step_e2e, ne2e) / ne2e
 
-    pta, sigs = nmfp_problem(wl)
-    F, D_total = wl["F"], wl["D_per_gpu"] * world
-    nm = fastfp_b200.NMFP(pta.psrs, sigs, device=local)
-    mats = (pta.Nvecs, pta.Ts, pta.TNTs)
+    # ---- checks (untimed) -----------------------------------------------------------------------
+    full = step_device()
+    torch.cuda.synchronize()
+    checks = {}
+    # (1) what the gather delivered for ANOTHER rank's shard == what this GPU computes alone for those bins
+    nb = (rank + 1) % world
+    lo2, hi2, _ = parallel.shard_bounds(F_total, nb, world)
+    if world == 1:  # one GPU: a slice from the middle of the grid recomputed as its own call
+        lo2 = F_total // 2
+        hi2 = F_total
+    k = min(4096, hi2 - lo2)
+    again = fp.calculate_Fp(freqs_dev[lo2:lo2 + k].contiguous(), *mats)
+    ok = bool(torch.equal(again, full[lo2:lo2 + k])) and bool(torch.isfinite(full).all())
+    checks["gathered_equals_single_gpu"] = {
+        "ok": ctx.all_ok(ok), "bins_per_rank": int(k),
+        "how": ("every rank recomputes the first bins of the next rank's shard alone and compares them with the "
+                "NCCL-gathered output bit for bit" if world > 1 else
+                "one GPU: a slice from the middle of the grid recomputed as a separate call, bit for bit")}
+    # (2) oracle spot check of the timed result (rank 0)
+    if rank == 0:
+        from oracle import fp_oracle
+
+        idx = spot_bins(F_total, pta.Tspan, freqs_np)
+        want = fp_oracle.fp_sweep(freqs_np[idx], pta.toas, pta.residuals, *mats)
+        got = full[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        rel = np.abs(got / want - 1.0)
+        well = freqs_np[idx] > 40.0 / pta.Tspan  # above the red-noise band: the plain 1e-10 applies
+        checks["oracle_spot"] = {
+            "bins": idx.tolist(), "max_rel_dev": float(rel.max()),
+            "max_rel_dev_well_conditioned": float(rel[well].max()) if well.any() else None,
+            "n_well_conditioned": int(well.sum()), "tolerance_well_conditioned": 1e-10,
+            "ok": bool((rel[well] <= 1e-10).all() and (rel <= 1e-6).all()),
+            "how": "oracle/fp_oracle.fp_sweep (NumPy restatement of fastfp/fastfp.py:69-92) on these bins of the "
+                   "gathered result of an untimed repeat of the step; bins inside the red-noise band (f < 40/Tspan) "
+                   "are ill-conditioned in the reference formula itself and held to 1e-6 here (tests/ bound them "
+                   "against the longdouble truth)"}
+
+    # dominant kernel alone, this rank's shard (for the roofline)
+    ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    shard = freqs_dev[lo:hi].contiguous()
+    nk = 3 if ms_step < 1000.0 else 1
+    fp.calculate_Fp(shard[:1024], *mats)
+    torch.cuda.synchronize()
+    ks.record()
+    for _ in range(nk):
+        fp.calculate_Fp(shard, *mats)
+    ke.record()
+    torch.cuda.synchronize()
+    kern_ms = ks.elapsed_time(ke) / nk
+    pack_bytes = pack.nbytes
+    fp.invalidate()  # free this workload's device pack before the next one is built
+
+    if rank != 0:
+        return None
+    evals_step = float(F_total) * wl["P"]
+    evals_kernel = float(hi - lo) * wl["P"]
+    hbm_peak, peak_src = measured_peaks()
+    ach_gbs = evals_kernel * bytes_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(key)
+    fp64_peak, _ = _cabi.fp64_peak(1, 20000, device=ctx.local)  # DMMA loop, same pipe as DFMA
+    ach_tf = evals_kernel * flops_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": evals_step / ms_step * 1e3, "unit": "evals/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(key, wl, world),
+        "run": {"parallelism": f"freq-shard x{world} ({hi - lo} bins on rank 0), pulsar arrays replicated, one NCCL "
+                               "all-gather of the bins",
+                "l2": "256 MiB buffer written between timed steps (L2 flush); packed inputs are "
+                      f"{pack_bytes / 2**20:.0f} MiB per GPU",
+                "pack_ms_one_time": pack_ms, "content_hash_ms_per_call": hash_ms,
+                "freqs_total": F_total, "evals_per_step": evals_step},
+        "e2e": {"value": evals_step / e2e_ms * 1e3, "unit": "evals/s", "ms_per_step": e2e_ms, "steps": ne2e,
+                "h2d_bytes_per_step": int(8 * F_total), "d2h_bytes_per_step": int(8 * F_total * world),
+                "cold": {"value": evals_step / (e2e_ms + pack_ms) * 1e3, "unit": "evals/s",
+                         "note": "first call of a process: one-time pack (upload + Cholesky + G build) + one step"}},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "checks": checks,
+        # The binding roofline: the contraction runs on the fp64 tensor path (DMMA), which shares one
+        # pipe with DFMA; peak = the same pipe measured on this GPU with a pure mma.m8n8k4.f64 loop.
+        "roofline": {"bound": "tensor", "pipe": "fp64 tensor path (DMMA; DFMA shares the pipe)",
+                     "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
+                                    "MEASURED_PEAKS.json holds no fp64 figure",
+                     "kernel": "fp_sweep_kernel (persistent, warp-specialised)", "kernel_ms": kern_ms,
+                     "flops_per_eval": flops_per_eval(wl["n"], M_BASIS),
+                     "note": "algorithmic flops (4m+10)n per eval: Y = G[s c] and the five weighted sums; the "
+                             "sincos generation that must also run on this pipe is not counted"},
+        "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference's streaming model); "
+                                 "every input is frequency-independent and L2-resident and tiles are reused "
+                                 "across the frequencies of a tile, so this effective figure exceeds 1 by "
+                                 "construction -- HBM is not the bound, measured DRAM traffic per launch is `traffic`"},
+    }
+    if with_cpu_baseline and world == 1:
+        rate, meta = cpu_reference_rate(wl, world=world, steps=1)
+        line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": meta["cores"], "kind": meta["kind"],
+                                "sample": meta["sample"]}
+    return line
+
+
+def run_nmfp(key, wl, ctx, steps, warmup, with_cpu_baseline):
+    """nmfp workload: NMFP.calculate_nmfp over (draws x frequencies); draws sharded across ranks."""
+    import fastfp_b200
+    from fastfp_b200 import _cabi, parallel, synth
+
+    torch, rank, world, dev = ctx.torch, ctx.rank, ctx.world, ctx.dev
+    pta, sigs, Nvecs, TNTs = nmfp_problem(wl)
+    F, D_total = wl["F"], total_D(wl, world)
+    nm = fastfp_b200.NMFP(pta.psrs, sigs, device=ctx.local)
+    mats = (Nvecs, pta.Ts, TNTs)
     t0 = time.perf_counter()
     pack = nm.prepare(*mats)
     torch.cuda.synchronize()
     pack_ms = (time.perf_counter() - t0) * 1e3
     samples = synth.draw_samples(pta, D_total)
-    freqs_host = torch.from_numpy(synth.nmfp_freqs(F, pta.Tspan)).pin_memory()
+    freqs_np = synth.nmfp_freqs(F, pta.Tspan)
+    freqs_host = torch.from_numpy(freqs_np).pin_memory()
     freqs_dev = freqs_host.to(dev)
     lo, hi, _ = parallel.shard_bounds(D_total, rank, world)
     mine = {k: v[lo:hi] for k, v in samples.items()}  # this rank's draws (the reference's host dict)
@@ -291,131 +570,131 @@ def run_nmfp(args, wl, rank, world, local):
         out_pinned.copy_(full, non_blocking=True)
         return out_pinned
 
-    flush_buf = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-
-    def timed(fn, steps):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
-        for a, b in ev:
-            flush_buf.fill_(1.0)
-            a.record()
-            fn()
-            b.record()
-        barrier()
-        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    few = {k: v[lo:min(hi, lo + 32)] for k, v in samples.items()}
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 1.5:  # rank-local spin-up (no collective: wall-clock bounded)
-        nm(freqs_dev, mine, *mats)
+        nm(freqs_dev, few, *mats)
         torch.cuda.synchronize()
-    barrier()
-    for _ in range(args.warmup):
+    ctx.barrier()
+    for _ in range(warmup):
         step_device()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
     launches0 = _cabi.kernel_launches()
-    total_ms = timed(step_device, args.steps)
+    total_ms = ctx.timed(step_device, steps)
     launches = _cabi.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
+    ms_step = total_ms / steps
+    ne2e = e2e_steps_for(steps, ms_step)
+    for _ in range(2 if ms_step < 1000.0 else 1):
         step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    e2e_ms = ctx.timed(step_e2e, ne2e) / ne2e
+
+    # ---- checks (untimed) -----------------------------------------------------------------------
+    full = step_device()
+    torch.cuda.synchronize()
+    checks = {}
+    nb = (rank + 1) % world
+    lo2, hi2, _ = parallel.shard_bounds(D_total, nb, world)
+    if world == 1:
+        lo2 = D_total // 2
+    k = min(8, hi2 - lo2)
+    again = nm(freqs_dev, {kk: v[lo2:lo2 + k] for kk, v in samples.items()}, *mats)
+    ok = bool(torch.equal(again, full[lo2:lo2 + k])) and bool(torch.isfinite(full).all())
+    checks["gathered_equals_single_gpu"] = {
+        "ok": ctx.all_ok(ok), "draws_per_rank": int(k),
+        "how": ("every rank recomputes the first draws of the next rank's shard alone and compares the rows with "
+                "the NCCL-gathered (D, F) output bit for bit" if world > 1 else
+                "one GPU: draws from the middle of the batch recomputed as a separate call, bit for bit")}
+    if rank == 0 and not wl.get("blockn"):
+        from oracle import fp_oracle
+
+        phi_args = [dict(psr_name=q.name, n_tm=ntm, Ffreqs=pta.Ffreqs, add_curn=True, curn_Ffreqs=pta.Ffreqs)
+                    for q, ntm in zip(pta.psrs, pta.n_tm)]
+        bins = np.array(sorted({0, min(F - 1, 45), F // 2, F - 2, F - 1} & set(range(F))), dtype=np.int64)
+        draws = sorted({0, D_total - 1})
+        sub = {kk: v[draws] for kk, v in samples.items()}
+        want = fp_oracle.nmfp_sweep(freqs_np[bins], sub, pta.toas, pta.residuals, pta.Nvecs, pta.Ts, pta.TNTs, phi_args)
+        got = full[draws][:, torch.from_numpy(bins).to(dev)].cpu().numpy()
+        rel = np.abs(got / want - 1.0)
+        well = freqs_np[bins] > 40.0 / pta.Tspan
+        checks["oracle_spot"] = {
+            "draws": draws, "bins": bins.tolist(), "max_rel_dev": float(rel.max()),
+            "max_rel_dev_well_conditioned": float(rel[:, well].max()) if well.any() else None,
+            "tolerance_well_conditioned": 1e-10,
+            "ok": bool((rel[:, well] <= 1e-10).all() and (rel <= 1e-5).all()),
+            "how": "oracle/fp_oracle.nmfp_sweep (restatement of fastfp/nmfp.py:57-119) on these (draw, bin) entries of "
+                   "the gathered result of an untimed repeat; the nmfp grid sits exactly on the red-noise Fourier "
+                   "frequencies k/Tspan, so bins with k < 40 are ill-conditioned in the reference formula itself"}
+    elif rank == 0:
+        checks["oracle_spot"] = {"ok": None, "how": "block-diagonal N: no reference implementation to restate "
+                                 "(fastfp/utils.py:29-31); parity of this path is pinned by tests/test_gpu_blockn.py and "
+                                 "the C5-shape test through the equivalent GP-basis formulation"}
 
     # per-stage kernel times of this rank's shard (events inside the library, on the launching stream)
     pack.stage_timing(True)
     stage = np.zeros(3)
-    for _ in range(3):
+    nrep = 3 if ms_step < 1000.0 else 1
+    for _ in range(nrep):
         nm(freqs_dev, mine, *mats)
         stage += np.array(pack.stage_ms())
-    stage /= 3
+    stage /= nrep
     pack.stage_timing(False)
+    nm.invalidate()  # free this workload's device pack before the next one is built
 
-    if rank == 0:
-        evals_step = float(F) * D_total * wl["P"]
-        ms_step = total_ms / args.steps
-        evals_rank = float(F) * (hi - lo) * wl["P"]
-        fl_total, fl_b = nmfp_flops_per_eval(wl["n"], M_BASIS, M_VAR, F, hi - lo)
-        fp64_peak, _ = _cabi.fp64_peak(1, 20000, device=local)
-        hbm_peak, peak_src = measured_peaks()
-        ach_b = evals_rank * fl_b / (stage[2] * 1e-3) / 1e12
-        ach_all = evals_rank * fl_total / (stage.sum() * 1e-3) / 1e12
-        ach_gbs = evals_rank * bytes_per_eval(wl["n"], M_BASIS) / (stage.sum() * 1e-3) / 1e9
-        nmfp_traffic = 1.595419e9 + 12.058112e6 if (F, hi - lo) == (1000, 1000) else None  # ncu, C3 shapes only
-        line = {
-            "metric": "Fp evals/sec (freqs x pulsars x draws)", "value": evals_step / ms_step * 1e3,
-            "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, wl, world),
-                       "parallelism": f"draw-shard x{world}, pulsar arrays replicated, one NCCL all-gather",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                       "inputs": "frequencies resident in HBM; the noise draws are the reference's host dict of "
-                                 f"(D,) arrays ({8 * (2 * wl['P'] + 2) * (hi - lo)} bytes per GPU), uploaded inside "
-                                 "every step of both timings",
-                       "pack_ms_one_time": pack_ms, "draws_total": D_total, "evals_per_step": evals_step},
-            "e2e": {"value": evals_step / (e2e_ms / args.steps) * 1e3, "unit": "evals/s",
-                    "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(8 * F + 8 * (2 * wl["P"] + 2) * (hi - lo)) * world,
-                    "d2h_bytes_per_step": int(8 * F * D_total * world)},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "pipe": "fp64 tensor path (DMMA; DFMA shares the pipe)",
-                         "kernel": "nmfp_stageB_kernel", "achieved": ach_b, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach_b / fp64_peak, "kernel_ms": float(stage[2]), "flops_per_eval": fl_b,
-                         "traffic": nmfp_traffic,
-                         "traffic_source": "profiles/r1_nmfp_ncu_summary.md (ncu dram__bytes_read+write, one launch)",
-                         "all_stages": {"achieved": ach_all, "frac": ach_all / fp64_peak,
-                                        "flops_per_eval": fl_total, "ms": float(stage.sum())},
-                         "stage_ms": {"stage_A_sweep": float(stage[0]), "factor": float(stage[1]),
-                                      "stage_B": float(stage[2])},
-                         "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
-                                        "MEASURED_PEAKS.json holds no fp64 figure",
-                         "note": "algorithmic flops 2 mv^2 + 10 mv per eval for stage B (exact triangle, mv = 60); the "
-                                 "kernel executes 64 8x4 blocks per 4 frequencies against 57 for the exact triangle"},
-            "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
-                             "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference re-streams every input "
-                                     "for each (frequency, draw)); here they are read once per frequency (stage A) "
-                                     "and the per-draw work runs on mv x mv blocks, so this effective figure exceeds "
-                                     "1 by construction -- HBM is not the bound"},
-        }
-        if not args.no_cpu_baseline and world == 1:
-            rate, meta = cpu_reference_rate_nmfp(wl, steps=1)
-            line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": meta["cores"], "kind": meta["kind"],
-                                    "sample": meta["sample"]}
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_reference(args, wl, rank, world):
     if rank != 0:
-        return
-    rate, meta = cpu_reference_rate(wl, steps=args.steps, warmup=min(args.warmup, 1),
-                                    target_s=min(12.0, 120.0 / max(1, args.steps + min(args.warmup, 1))))
+        return None
+    evals_step = float(F) * D_total * wl["P"]
+    evals_rank = float(F) * (hi - lo) * wl["P"]
+    fl_total, fl_b = nmfp_flops_per_eval(wl["n"], M_BASIS, M_VAR, F, hi - lo)
+    fp64_peak, _ = _cabi.fp64_peak(1, 20000, device=ctx.local)
+    hbm_peak, peak_src = measured_peaks()
+    ach_b = evals_rank * fl_b / (stage[2] * 1e-3) / 1e12
+    ach_all = evals_rank * fl_total / (stage.sum() * 1e-3) / 1e12
+    ach_gbs = evals_rank * bytes_per_eval(wl["n"], M_BASIS) / (stage.sum() * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(key)
     line = {
-        "impl": "reference", "metric": "Fp evals/sec (freqs x pulsars x draws)", "value": rate, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": meta["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, wl, args.gpus), "parallelism": "cpu-host"},
-        "cpu_baseline": {"value": rate, "unit": "evals/s", "cores": meta["cores"], "kind": meta["kind"],
-                         "sample": meta["sample"]},
-        "e2e": {"value": rate, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "metric": METRIC, "value": evals_step / ms_step * 1e3,
+        "unit": "evals/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(key, wl, world),
+        "run": {"parallelism": f"draw-shard x{world} ({hi - lo} draws on rank 0), pulsar arrays replicated, one NCCL "
+                               f"all-gather of the (D, F) rows ({8 * F * (hi - lo) / 1e6:.1f} MB per rank)",
+                "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                "inputs": "frequencies resident in HBM; the noise draws are the reference's host dict of "
+                          f"(D,) arrays ({8 * (2 * wl['P'] + 2) * (hi - lo)} bytes per GPU), uploaded inside "
+                          "every step of both timings",
+                "pack_ms_one_time": pack_ms, "draws_total": D_total, "evals_per_step": evals_step},
+        "e2e": {"value": evals_step / e2e_ms * 1e3, "unit": "evals/s", "ms_per_step": e2e_ms, "steps": ne2e,
+                "h2d_bytes_per_step": int(8 * F + 8 * (2 * wl["P"] + 2) * (hi - lo)) * world,
+                "d2h_bytes_per_step": int(8 * F * D_total * world)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "checks": checks,
+        "roofline": {"bound": "tensor", "pipe": "fp64 tensor path (DMMA; DFMA shares the pipe)",
+                     "kernel": "nmfp_stageB_kernel", "achieved": ach_b, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": ach_b / fp64_peak, "kernel_ms": float(stage[2]), "flops_per_eval": fl_b,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "all_stages": {"achieved": ach_all, "frac": ach_all / fp64_peak,
+                                    "flops_per_eval": fl_total, "ms": float(stage.sum())},
+                     "stage_ms": {"stage_A_sweep": float(stage[0]), "factor": float(stage[1]),
+                                  "stage_B": float(stage[2])},
+                     "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
+                                    "MEASURED_PEAKS.json holds no fp64 figure",
+                     "note": "algorithmic flops 2 mv^2 + 10 mv per eval for stage B (exact triangle, mv = 60)"},
+        "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
+                         "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference re-streams every input "
+                                 "for each (frequency, draw)); here they are read once per frequency (stage A) "
+                                 "and the per-draw work runs on mv x mv blocks, so this effective figure exceeds "
+                                 "1 by construction -- HBM is not the bound"},
     }
-    emit(line)
-
-
-def workload_name(key, wl, gpus):
-    if wl.get("nmfp"):
-        return (f"{key}: noise-marginalised Fp, {wl['P']} pulsars x {wl['n']} TOAs, m={M_BASIS} (12 timing-model "
-                f"+ 60 red-noise/CURN Fourier), {wl['F']} frequencies x {wl['D_per_gpu']} noise draws per GPU x "
-                f"{gpus} GPU(s), fp64")
-    return (f"{key}: Fp sweep, {wl['P']} pulsars x {wl['n']} TOAs, m={M_BASIS} (12 timing-model + 60 Fourier), "
-            f"{wl['F_per_gpu']} frequencies per GPU x {gpus} GPU(s), red+white Woodbury C, fp64")
+    if with_cpu_baseline and world == 1:
+        rate, meta = cpu_reference_rate_nmfp(wl, world=world, steps=1)
+        line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": meta["cores"], "kind": meta["kind"],
+                                "sample": meta["sample"]}
+    return line
 
 
 _JSON_OUT = None
@@ -435,170 +714,53 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="C2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=None)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    wl = WORKLOADS[args.workload]
+    key = args.workload or "C4"
+    wl = WORKLOADS[key]
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        (run_reference_nmfp if wl.get("nmfp") else run_reference)(args, wl, rank, world)
+        run_reference(args, key, wl, rank, world)
         return
-    if wl.get("nmfp"):
-        run_nmfp(args, wl, rank, world, local)
-        return
+    if os.environ.get("FASTFP_DBG") and not os.environ.get("FASTFP_BENCH_ALLOW_DBG"):
+        raise SystemExit("FASTFP_DBG is set: it only acts on developer builds that can switch work off; unset it")
+    if os.environ.get("FASTFP_B200_NVCC_FLAGS") and not os.environ.get("FASTFP_BENCH_ALLOW_DBG"):
+        raise SystemExit("FASTFP_B200_NVCC_FLAGS is set: bench.py only measures the library as shipped")
 
-    import torch
-    import torch.distributed as dist
-
-    import fastfp_b200
-    from fastfp_b200 import _cabi, parallel, synth
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the Fp hot path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- build the workload (host, untimed) and pack it onto this rank's GPU ------------------
-    pta = synth.make_pta(wl["P"], wl["n"])
-    F_total = wl["F_per_gpu"] * world
-    freqs_host = torch.from_numpy(synth.fp_freqs(F_total)).pin_memory()
-    fp = fastfp_b200.FastFp(pta.psrs, device=local)
-    t0 = time.perf_counter()
-    pack = fp.prepare(pta.Nvecs, pta.Ts, pta.sigmas)
-    torch.cuda.synchronize()
-    pack_ms = (time.perf_counter() - t0) * 1e3
-    mats = (pta.Nvecs, pta.Ts, pta.sigmas)
-    freqs_dev = freqs_host.to(dev)
-    lo, hi, per = parallel.shard_bounds(F_total, rank, world)
-
-    def step_device():
-        """inputs resident in HBM: sweep the shard, all-gather the bins"""
-        return parallel.sharded_sweep(lambda f: fp.calculate_Fp(f, *mats), freqs_dev)
-
-    out_pinned = torch.empty(F_total, dtype=torch.float64).pin_memory()
-
-    def step_e2e():
-        """public API with host buffers: H2D of the shard's frequencies, sweep, gather, D2H of Fp"""
-        f = freqs_host[lo:hi].to(dev, non_blocking=True)
-        full = parallel.sharded_sweep(lambda _: fp.calculate_Fp(f, *mats), freqs_dev)
-        out_pinned.copy_(full, non_blocking=True)
-        return out_pinned
-
-    flush_buf = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-
-    def timed(fn, steps):
-        total = 0.0
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
-        for a, b in ev:
-            flush_buf.fill_(1.0)  # L2 flush, outside the timed bracket
-            a.record()
-            fn()
-            b.record()
-        barrier()
-        total = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([total], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # clock spin-up (the SM clock needs ~0.4 s of load to leave its idle state), then W warm-ups. The
-    # spin-up is wall-clock bounded, so it must stay rank-local: no collective inside (ranks would run
-    # different numbers of them and deadlock).
-    shard0 = freqs_dev[lo:hi].contiguous()
-    t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 1.5:
-        fp.calculate_Fp(shard0, *mats)
-        torch.cuda.synchronize()
-    barrier()
-    for _ in range(args.warmup):
-        step_device()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = _cabi.kernel_launches()
-    total_ms = timed(step_device, args.steps)
-    launches = _cabi.kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
-
-    # dominant kernel alone, this rank's shard (for the roofline)
-    ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    shard = freqs_dev[lo:hi].contiguous()
-    torch.cuda.synchronize()
-    ks.record()
-    for _ in range(3):
-        fp.calculate_Fp(shard, *mats)
-    ke.record()
-    torch.cuda.synchronize()
-    kern_ms = ks.elapsed_time(ke) / 3
-
-    if rank == 0:
-        evals_step = float(F_total) * wl["P"]
-        ms_step = total_ms / args.steps
-        value = evals_step / ms_step * 1e3
-        e2e_value = evals_step / (e2e_ms / args.steps) * 1e3
-        evals_kernel = float(hi - lo) * wl["P"]
-        hbm_peak, peak_src = measured_peaks()
-        ach_gbs = evals_kernel * bytes_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e9
-        traffic, traffic_src = measured_traffic(args.workload)
-        fp64_peak, _ = _cabi.fp64_peak(1, 20000, device=local)  # DMMA loop, same pipe as DFMA
-        ach_tf = evals_kernel * flops_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e12
-        line = {
-            "metric": "Fp evals/sec (freqs x pulsars x draws)", "value": value, "unit": "evals/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, wl, world),
-                       "parallelism": f"freq-shard x{world}, pulsar arrays replicated, one NCCL all-gather",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); packed inputs are "
-                             f"{pack.nbytes / 2**20:.0f} MiB per GPU",
-                       "pack_ms_one_time": pack_ms, "freqs_total": F_total, "evals_per_step": evals_step},
-            "e2e": {"value": e2e_value, "unit": "evals/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(8 * F_total), "d2h_bytes_per_step": int(8 * F_total * world)},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            # The binding roofline: the contraction runs on the fp64 tensor path (DMMA), which shares one
-            # pipe with DFMA; peak = the same pipe measured on this GPU with a pure mma.m8n8k4.f64 loop.
-            "roofline": {"bound": "tensor", "pipe": "fp64 tensor path (DMMA; DFMA shares the pipe)",
-                         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                         "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
-                                        "MEASURED_PEAKS.json holds no fp64 figure",
-                         "kernel": "fp_sweep_kernel (persistent, warp-specialised)", "kernel_ms": kern_ms,
-                         "flops_per_eval": flops_per_eval(wl["n"], M_BASIS),
-                         "note": "algorithmic flops (4m+10)n per eval: Y = G[s c] and the five weighted sums; the "
-                                 "sincos generation that must also run on this pipe is not counted"},
-            "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                             "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference's streaming model); "
-                                     "every input is frequency-independent and L2-resident and tiles are reused "
-                                     "across 64 frequencies, so this effective figure exceeds 1 by construction -- "
-                                     "HBM is not the bound, measured DRAM traffic per launch is `traffic`"},
-        }
-        if not args.no_cpu_baseline and world == 1:
-            rate, meta = cpu_reference_rate(wl, steps=1)
-            line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": meta["cores"], "kind": meta["kind"],
-                                    "sample": meta["sample"]}
+    ctx = Ctx(rank, world, local)
+    runner = run_nmfp if wl["kind"] == "nmfp" else run_fp
+    line = runner(key, wl, ctx, args.steps, args.warmup, not args.no_cpu_baseline)
+    if args.workload is None and not args.no_secondary:
+        sec = {}
+        for k2 in ("C2", "C3"):
+            w2 = WORKLOADS[k2]
+            r2 = run_nmfp if w2["kind"] == "nmfp" else run_fp
+            res = r2(k2, w2, ctx, min(args.steps, 10), 3, False)
+            if res is not None:
+                sec[k2] = res
+        if line is not None:
+            line["secondary"] = sec
+    if line is not None:
+        bad = [name for name, c in line.get("checks", {}).items() if c.get("ok") is False]
+        for k2, l2 in line.get("secondary", {}).items():
+            bad += [f"{k2}.{name}" for name, c in l2.get("checks", {}).items() if c.get("ok") is False]
+        line["checks_failed"] = bad
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+        if bad:
+            print(f"bench.py: result checks FAILED: {bad}", file=sys.stderr)
+            ctx.close()
+            raise SystemExit(3)
+    ctx.close()
 
 
 if __name__ == "__main__":

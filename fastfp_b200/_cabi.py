@@ -59,6 +59,8 @@ SYMBOLS = {
     "fastfp_pack_bytes": (C.c_int64, [C.c_void_p]),
     "fastfp_pack_num_pulsars": (C.c_int, [C.c_void_p]),
     "fastfp_pack_mvar_total": (C.c_int64, [C.c_void_p]),
+    "fastfp_pack_factor_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "fastfp_hash64": (C.c_uint64, [C.c_void_p, C.c_int64, C.c_uint64]),
     "fastfp_kernel_launches": (C.c_int64, []),
     "fastfp_xcy": (
         C.c_int,
@@ -165,12 +167,38 @@ def _check_lists(toas, residuals, Nvecs, Ts, mats, what):
     return P, n, m, toas, residuals, Nvecs, Ts, mats
 
 
+def hash64(a: np.ndarray, seed: int = 0) -> int:
+    """64-bit hash of every byte of a C-contiguous host array (``fastfp_hash64``)."""
+    return int(load().fastfp_hash64(C.c_void_p(a.ctypes.data), a.nbytes, C.c_uint64(seed & (2**64 - 1))))
+
+
 class Pack:
     """Owner of one ``fastfp_pack_t*``: the device-resident packed pulsar array."""
 
     def __init__(self, handle, P: int, device: int, nmfp: bool, n, m):
         self._h, self.P, self.device, self.nmfp = handle, P, device, nmfp
         self.n, self.m = list(n), list(m)
+        self._warn_if_not_spd()
+
+    def factor_info(self):
+        """Per-pulsar status of the one-time Cholesky (0 = fine, j+1 = pivot j not positive)."""
+        info = (C.c_int32 * self.P)()
+        rc = load().fastfp_pack_factor_info(self._h, info)
+        if rc < 0:
+            check(rc)
+        return list(info)
+
+    def _warn_if_not_spd(self):
+        bad = [(p, v) for p, v in enumerate(self.factor_info()) if v]
+        if bad:
+            import warnings
+
+            what = "Sigma" if not self.nmfp else "the draw-independent block of Sigma"
+            warnings.warn(
+                "fastfp_b200: " + what + " is not numerically symmetric positive definite for pulsar(s) "
+                + ", ".join(f"{p} (pivot {v - 1})" for p, v in bad)
+                + "; their terms are NaN. The sweep path factorises Sigma = L L^T (lower triangle); the "
+                "reference's general LU solve is only available through get_xCy.", RuntimeWarning, stacklevel=3)
 
     @classmethod
     def create_fp(cls, toas, residuals, Nvecs, Ts, sigmas, device: int = 0, stream: int = 0) -> "Pack":

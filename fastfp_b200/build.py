@@ -18,9 +18,12 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libfastfp_b200.so")
 SOURCES = ["cabi.cu", "precompute.cu", "fp_sweep.cu", "fp_sweep_w1.cu", "fp_sweep_w2.cu", "fp_sweep_w4.cu",
-           "fp_sweep_wide.cu", "nmfp.cu", "xcy.cu", "microbench.cu"]
+           "fp_sweep_wide.cu", "nmfp.cu", "xcy.cu", "microbench.cu", "hostutil.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-fmad=true"]
+# developer builds only (e.g. FASTFP_B200_NVCC_FLAGS=-DFFP_DEBUG_SWITCHES for tools/dbg_split.sh); the
+# shipped library is built without it and bench.py refuses to run a library built with extra flags
+EXTRA = os.environ.get("FASTFP_B200_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:
@@ -37,7 +40,7 @@ def _digest() -> str:
         if os.path.isfile(path):
             with open(path, "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
-    h.update(" ".join(ARCH + FLAGS).encode())
+    h.update(" ".join(ARCH + FLAGS + EXTRA).encode())
     return h.hexdigest()
 
 
@@ -52,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(pair):
         src, obj = pair
-        cmd = [nvcc, *ARCH, *FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH, *FLAGS, *EXTRA, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -333,6 +333,16 @@ void fastfp_pack_destroy(fastfp_pack_t* pack) { pack_free(pack); }
 int64_t fastfp_pack_bytes(const fastfp_pack_t* pack) { return pack ? pack->bytes : 0; }
 int fastfp_pack_num_pulsars(const fastfp_pack_t* pack) { return pack ? pack->P : 0; }
 int64_t fastfp_pack_mvar_total(const fastfp_pack_t* pack) { return pack ? pack->mvar_total : 0; }
+int fastfp_pack_factor_info(const fastfp_pack_t* pack, int32_t* info) {
+  if (!pack) { set_error("fastfp_pack_factor_info: null pack"); return FASTFP_ERR_INVALID; }
+  int bad = 0;
+  for (int p = 0; p < pack->P; ++p) {
+    const int v = p < (int)pack->info.size() ? pack->info[p] : 0;
+    if (info) info[p] = v;
+    bad += v != 0;
+  }
+  return bad;
+}
 
 // Frequencies are processed in batches so the (P, F_batch) term buffer stays bounded.
 static const int64_t kTermBudgetDoubles = 1LL << 27;  // 1 GiB

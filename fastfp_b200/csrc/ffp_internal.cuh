@@ -127,6 +127,7 @@ struct fastfp_pack {
   double* d_packets = nullptr;  // [sum_p nch_p][PK_p]
   double* d_L = nullptr;        // Cholesky factors (Fp) / fixed-block factors (nmfp)
   int* d_info = nullptr;        // per-pulsar factorisation status
+  std::vector<int> info;        // host copy, read back when the pack is built (fastfp_pack_factor_info)
   double* d_slab = nullptr;     // level-2 accumulation scratch, one slab per resident CTA
   unsigned int* d_counter = nullptr;  // persistent-CTA work counter
   int64_t bytes = 0;

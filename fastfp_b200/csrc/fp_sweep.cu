@@ -33,7 +33,9 @@ __global__ void reduce_terms_kernel(const double* __restrict__ terms, int P, int
 
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
                     cudaStream_t st, const NmfpOut* nm) {
-  static const int dbg = getenv("FASTFP_DBG") ? atoi(getenv("FASTFP_DBG")) : 0;  // profiling only
+#ifdef FFP_DEBUG_SWITCHES  // profiling builds only; the shipped library is compiled without it
+  static const int dbg = getenv("FASTFP_DBG") ? atoi(getenv("FASTFP_DBG")) : 0;
+#endif
   SweepArgs a{};
   a.packets = pk->d_packets;
   a.meta = pk->d_meta;
@@ -46,7 +48,9 @@ int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, dou
   a.A = nm ? nm->A : nullptr;
   a.mvmax = nm ? nm->mvmax : 0;
   a.done_mask = pk->d_done_mask;
+#ifdef FFP_DEBUG_SWITCHES
   a.dbg = dbg;
+#endif
   for (const Group& g : pk->groups) {
     int rc;
     if (g.cfg.wmw == 4) rc = dispatch_sweep_wide(pk, g, a, nm != nullptr, st);

@@ -1,5 +1,6 @@
-// The frequency-sweep kernel: a persistent, warp-specialised CTA (8 producer + 4 consumer warps,
-// one CTA per SM) takes (pulsar, frequency-tile) work items from an atomic counter.
+// The frequency-sweep kernel (fp64 DMMA formulation): a persistent, warp-specialised CTA -- SweepCfg::NWC
+// consumer (MMA) warps + SweepCfg::NWP producer (sincos) warps, 8 + 16 = 768 threads by default, one CTA
+// per SM -- takes (pulsar, frequency-tile) work items from an atomic counter.
 //
 // Replaces the body of FastFp.calculate_Fp under jax.vmap (reference fastfp/fastfp.py:69-92,
 // examples/run_fp.py:63) -- and, with NMFP = true, the draw-independent part of
@@ -19,10 +20,10 @@
 //                  does at fastfp.py:90); term = 0.5 * N . M^-1 N.
 //
 // Producers and consumers are decoupled by full/empty mbarriers, so the dependent sincos chains of
-// the producers interleave with the consumers' MMAs on the shared fp64 pipe at run time. Each SM
-// sub-partition hosts one consumer warp and two producer warps (so the producers win most issue
-// arbitration rounds and never starve the MMA stream of S tiles); the register file is split with
-// setmaxnreg (consumers 216, producers 112 registers per thread).
+// the producers interleave with the consumers' MMAs on the shared fp64 pipe at run time. With the default
+// split each SM sub-partition hosts two consumer warps and four producer warps (the producers' DFMAs queue
+// behind the MMAs on the shared pipe, so it takes that many to keep the S ring full); the register file is
+// split with setmaxnreg (SweepCfg::CREGS / PREGS = 120 / 56 registers per thread out of the 768 x 80 pool).
 //
 // The f^(-1/3) prefactor of fastfp.py:78-79 scales N by a and M by a^2 and cancels exactly in
 // N^T M^-1 N; it is not applied (f <= 0 still yields NaN as in the reference).
@@ -52,8 +53,16 @@ struct SweepArgs {
   double* A;              // nmfp: [P][ceil(F/32)][5][32]
   int mvmax;
   const unsigned char* done_mask;  // block-N packs: per chunk, which of the 8 epoch slots end there
-  int dbg;
+#ifdef FFP_DEBUG_SWITCHES
+  int dbg;  // profiling builds only (tools/dbg_split.sh): bit 0 producers' math off, 1 MMAs off, 2 level-2 flush off
+#endif
 };
+// The shipped library has no run-time switch that could skip work: the bits are a compile-time zero.
+#ifdef FFP_DEBUG_SWITCHES
+#define FFP_DBG(ar, bit) ((ar).dbg & (bit))
+#else
+#define FFP_DBG(ar, bit) 0
+#endif
 
 // D(8x8) += A(8x4) . B(4x8), fp64. Lane l holds A[l>>2][l&3], B[l&3][l>>2], D[l>>2][2*(l&3)+{0,1}].
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -155,7 +164,7 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
       if (k >= C::SST) mbar_wait(&sm.s_empty[k % C::SST], ((k / C::SST) - 1) & 1u);
       const double* pk = sm.Vring + (k % VST) * C::VEC;
       double* sb = sm.Sring + (k % C::SST) * C::ST + sofs;
-      if (!(ar.dbg & 1) && pw < C::NACTIVE) {
+      if (!FFP_DBG(ar, 1) && pw < C::NACTIVE) {
         if (fast) {
           // straight-line: every phase of this tile is inside the Cody-Waite range (checked once per
           // work item against the pulsar's largest |TOA|), so there is no per-element test
@@ -209,7 +218,7 @@ __device__ __forceinline__ void producer_loop(const SweepArgs& ar, SweepSmem<C>&
         mbar_arrive(&sm.s_full[k % C::SST]);
         mbar_arrive(&sm.v_empty[k % VST]);
       }
-      if ((c + 1) % C::FLUSH == 0 && c + 1 < nch && !(ar.dbg & 4)) {
+      if ((c + 1) % C::FLUSH == 0 && c + 1 < nch && !FFP_DBG(ar, 4)) {
 #pragma unroll
         for (int xx = 0; xx < XW; ++xx)
 #pragma unroll
@@ -342,7 +351,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
 #pragma unroll
           for (int q = 0; q < NNB; ++q) b1[q] = 0.0;
         }
-        if (!(ar.dbg & 2)) {
+        if (!FFP_DBG(ar, 2)) {
 #pragma unroll
           for (int r = 0; r < NMBW; ++r)
 #pragma unroll
@@ -371,7 +380,7 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
           }
         }
       }
-      if ((c + 1) % C::FLUSH == 0 && c + 1 < nch && !(ar.dbg & 4)) {
+      if ((c + 1) % C::FLUSH == 0 && c + 1 < nch && !FFP_DBG(ar, 4)) {
         // fold the level-1 sums into the level-2 totals of this CTA's scratch slab
 #pragma unroll
         for (int r = 0; r < NMBW; ++r)

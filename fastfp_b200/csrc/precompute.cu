@@ -158,6 +158,11 @@ int launch_fp_precompute(fastfp_pack* pk, const double* d_toas, const double* d_
   g_launches += 4;
   FFP_CUDA(cudaGetLastError());
   FFP_CUDA(cudaStreamSynchronize(st));
+  // the factorisation status comes back with the pack: a non-positive pivot means Sigma was not numerically
+  // SPD; the factor then carries NaN, which propagates like the reference's non-raising solve -- but the
+  // caller can ask which pulsar it was (fastfp_pack_factor_info; the Python mirror warns)
+  pk->info.assign(P, 0);
+  FFP_CUDA(cudaMemcpy(pk->info.data(), pk->d_info, sizeof(int) * P, cudaMemcpyDeviceToHost));
   if (!d_ur_keep) FFP_CUDA(cudaFree(d_ur));
   return 0;
 }

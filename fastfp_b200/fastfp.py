@@ -22,21 +22,20 @@ import numpy as np
 from . import _cabi
 
 
-def _plain(a):
-    """array view of an Nvec entry for fingerprinting (block-N objects: their diagonal part)"""
-    return np.asarray(a._nvec if hasattr(a, "_nvec") else a)
-
-
 def _fingerprint(lists) -> tuple:
-    """Cheap identity + content key so a pack is rebuilt when the caller passes new data
-    (per array: address, shape and a 16-point content sample; no full pass over the data)."""
+    """Content key of the caller's lists: shape + a 64-bit hash of EVERY byte of every array
+    (``fastfp_hash64``: memory-bandwidth class, threaded for large arrays). The reference is a pure function
+    of these arguments (``fastfp/fastfp.py:52``), so the cached device pack must be rebuilt whenever any
+    entry changes -- including in-place edits, which an address- or sample-based key cannot see."""
     key = []
     for lst in lists:
-        key.append((id(lst), len(lst)))
+        key.append(len(lst))
         for a in lst:
-            a = _plain(a)
-            flat = a.reshape(-1)
-            key.append((a.__array_interface__["data"][0], a.shape, flat[:: max(1, flat.size // 16)][:16].tobytes()))
+            parts = [a._nvec, a._jvec, np.asarray([(s.start, s.stop) for s in a._slices], dtype=np.int64)] \
+                if hasattr(a, "_nvec") else [a]
+            for x in parts:
+                x = np.ascontiguousarray(x)
+                key.append((x.shape, x.dtype.str, _cabi.hash64(x, seed=len(key))))
     return tuple(key)
 
 
@@ -67,10 +66,18 @@ class FastFp(object):
         self._pack_key = None
 
     # -- packing (one-time, frequency-independent precompute on the device) -----------------
-    def prepare(self, Nvecs, Ts, sigmas):
-        """Upload and pre-reduce the per-pulsar arrays; cached until different arrays are passed."""
+    def invalidate(self):
+        """Drop the cached device pack (the next call rebuilds it)."""
+        if self._pack is not None:
+            self._pack.close()
+        self._pack, self._pack_key = None, None
+
+    def prepare(self, Nvecs, Ts, sigmas, force=False):
+        """Upload and pre-reduce the per-pulsar arrays. The pack is cached and keyed on the full contents
+        of the three lists (every byte is hashed on each call), so passing different arrays -- or the same
+        arrays edited in place -- rebuilds it; ``force=True`` rebuilds unconditionally."""
         key = _fingerprint((Nvecs, Ts, sigmas))
-        if self._pack is None or key != self._pack_key:
+        if force or self._pack is None or key != self._pack_key:
             if self._pack is not None:
                 self._pack.close()
             from . import blockn

@@ -227,9 +227,16 @@ class NMFP(object):
             sigmas.append(np.asarray(TNT, dtype=np.float64) + np.diag(phiinv))
         return sigmas
 
-    def prepare(self, Nvecs, Ts, TNTs):
+    def invalidate(self):
+        """Drop the cached device pack (the next call rebuilds it)."""
+        if self._pack is not None:
+            self._pack.close()
+        self._pack, self._pack_key = None, None
+
+    def prepare(self, Nvecs, Ts, TNTs, force=False):
+        """Cached like :meth:`FastFp.prepare`: keyed on a hash of every byte of the three lists."""
         key = _fingerprint((Nvecs, Ts, TNTs))
-        if self._pack is None or key != self._pack_key:
+        if force or self._pack is None or key != self._pack_key:
             if self._pack is not None:
                 self._pack.close()
             fixed = [sig.fixed_phi() for sig in self.rn_sigs]
@@ -293,6 +300,8 @@ class NMFP(object):
         if _is_cuda_tensor(fgw):
             if fgw.dtype != torch.float64:
                 raise TypeError("fgw tensor must be float64")
+            if fgw.device.index != self.device:
+                raise ValueError(f"fgw is on {fgw.device}, the pack on cuda:{self.device}")
             f = fgw.contiguous().reshape(-1)
             out = torch.empty((D, f.shape[0]), dtype=torch.float64, device=dev)
             pack.nmfp_sweep((f.data_ptr(), f.shape[0]), phiinv.data_ptr(), D, out=out.data_ptr(), stream=stream)

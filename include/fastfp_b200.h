@@ -134,6 +134,16 @@ void fastfp_pack_destroy(fastfp_pack_t* pack);
 int64_t fastfp_pack_bytes(const fastfp_pack_t* pack);    /* device bytes held */
 int fastfp_pack_num_pulsars(const fastfp_pack_t* pack);
 int64_t fastfp_pack_mvar_total(const fastfp_pack_t* pack); /* sum_p m_var[p] (nmfp packs) */
+/* Status of the one-time Cholesky of Sigma_p (plain Fp) or of its draw-independent block (nmfp):
+ * info[p] = 0, or j+1 when pivot j was not positive -- Sigma_p is then not numerically symmetric positive
+ * definite (the sweep path factorises Sigma = L L^T and reads its lower triangle; the reference's
+ * jnp.linalg.solve, fastfp/utils.py:54, accepts any non-singular matrix, and so does fastfp_xcy). The
+ * statistic of such a pulsar is NaN, as a singular Sigma gives in the reference; nothing is raised.
+ * Returns the number of pulsars with info != 0 (>= 0), or a negative error code; info may be NULL. */
+int fastfp_pack_factor_info(const fastfp_pack_t* pack, int32_t* info);
+/* 64-bit content hash of a host buffer (multi-threaded for large buffers; deterministic): what the Python
+ * mirror uses to key its pack cache on every byte of the caller's arrays. */
+uint64_t fastfp_hash64(const void* data, int64_t nbytes, uint64_t seed);
 int64_t fastfp_kernel_launches(void); /* kernels launched by this library so far (process-wide) */
 /* measurement aid: with enable != 0 every later fastfp_nmfp_sweep on this pack brackets its three
  * stages with CUDA events on the caller's stream and synchronises at the end; fastfp_nmfp_stage_ms

@@ -116,3 +116,67 @@ def test_compat_package_resolves_reference_import_paths():
         sys.path.remove(root)
         for k in [k for k in sys.modules if k == "fastfp" or k.startswith("fastfp.")]:
             del sys.modules[k]
+
+
+def test_vmap_output_axes_follow_the_nesting_order_and_axes_are_validated():
+    """jax.vmap semantics around the natively batched call: the reference's nesting (frequencies inside,
+    draws outside; examples/run_nmfp.py:265-266) gives (D, F), the opposite nesting (F, D); an argument marked
+    0 needs a leading axis, one marked None must not have one."""
+    def native(fgw, samples, a, b, c):  # what NMFP.calculate_nmfp returns for batched input: (D, F)
+        D = len(next(iter(samples.values())))
+        return np.arange(D)[:, None] * 100.0 + np.asarray(fgw)[None, :]
+
+    f, s = np.arange(3.0), {"x": np.zeros(2), "y": np.zeros(2)}
+    vf = vmap(native, in_axes=(0, None, None, None, None))
+    vg = vmap(vf, in_axes=(None, 0, None, None, None))
+    assert vg(f, s, 0, 0, 0).shape == (2, 3)
+    wf = vmap(native, in_axes=(None, 0, None, None, None))
+    wg = vmap(wf, in_axes=(0, None, None, None, None))
+    out = wg(f, s, 0, 0, 0)
+    assert out.shape == (3, 2)
+    np.testing.assert_array_equal(out, vg(f, s, 0, 0, 0).T)
+    with pytest.raises(ValueError, match="no leading axis"):
+        vg(1e-8, s, 0, 0, 0)
+    with pytest.raises(ValueError, match="no leading axis"):
+        vg(f, {"x": 1.0, "y": 2.0}, 0, 0, 0)
+    with pytest.raises(ValueError, match="unbatched"):
+        vmap(native, in_axes=(None, 0, None, None, None))(f, s, 0, 0, 0)  # frequency array, not mapped
+    with pytest.raises(ValueError, match="disagree"):
+        vg(f, {"x": np.zeros(2), "y": np.zeros(3)}, 0, 0, 0)
+    with pytest.raises(ValueError, match="already mapped"):
+        vmap(vf, in_axes=(0, None, None, None, None))
+
+
+def test_pack_cache_key_sees_every_byte():
+    """the pack cache key must change for ANY in-place edit of the caller's arrays."""
+    from fastfp_b200.blockn import BlockNvec
+    from fastfp_b200.fastfp import _fingerprint
+
+    pta = synth.make_pta(2, [301, 257], n_tm=3, ncomps=4)
+    lists = (pta.Nvecs, pta.Ts, pta.sigmas)
+    k0 = _fingerprint(lists)
+    assert _fingerprint(lists) == k0  # deterministic
+    assert _fingerprint(([a.copy() for a in pta.Nvecs], pta.Ts, pta.sigmas)) == k0  # content, not identity
+    rng = np.random.default_rng(0)
+    for arr in (pta.Nvecs[1], pta.Ts[0], pta.sigmas[1]):
+        flat = arr.reshape(-1)
+        for _ in range(8):  # single-element edits at random positions, each one must be seen
+            i = int(rng.integers(flat.size))
+            old = flat[i]
+            flat[i] = np.nextafter(old, np.inf)
+            assert _fingerprint(lists) != k0, i
+            flat[i] = old
+    assert _fingerprint(lists) == k0
+    # block-N objects: the diagonal part, the epoch variances and the slices all enter
+    B = BlockNvec(pta.Nvecs[0].copy(), [slice(0, 4), slice(8, 11)], np.array([1e-13, 2e-13]))
+    kb = _fingerprint(([B, pta.Nvecs[1]], pta.Ts, pta.sigmas))
+    assert kb != k0
+    B.jvec[1] *= 1.0000001
+    assert _fingerprint(([B, pta.Nvecs[1]], pta.Ts, pta.sigmas)) != kb
+    # the hash itself: thread-count independent block structure, seed and length sensitive
+    big = rng.standard_normal(3_000_017)
+    h = _cabi.hash64(big)
+    assert h == _cabi.hash64(big.copy()) and h != _cabi.hash64(big, seed=1) and h != _cabi.hash64(big[:-1])
+    swapped = big.copy()
+    swapped[[5, 2_000_000]] = swapped[[2_000_000, 5]]
+    assert _cabi.hash64(swapped) != h

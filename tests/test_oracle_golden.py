@@ -125,3 +125,37 @@ def test_get_sigmas_and_nmfp_goldens(golden):
                        _phi_args(g, True))
     allow = 1e-10 * np.abs(g["truth_nmfp_curn"]) + 256 * EPS * g["cond_curn"]
     assert np.all(np.abs(bat - g["truth_nmfp_curn"]) <= allow)
+
+
+def test_block_n_truth_equals_the_gp_basis_truth():
+    """oracle/truth.fp_sweep_truth_blockn (Sherman-Morrison in longdouble) is the same quantity as the
+    reference-implemented GP-basis model (epoch-indicator columns appended to T, fastfp/nmfp.py:277-282)
+    evaluated by fp_sweep_truth: pinned here at a size where the O((m + n_epoch)^3) form runs."""
+    from fastfp_b200 import synth
+    from oracle import truth
+
+    pta = synth.make_pta(2, [203, 160], n_tm=[4, 5], ncomps=6, seed=3)
+    rng = np.random.default_rng(1)
+    blocks, Text, sig_ext, phiinvs = [], [], [], []
+    for p in range(2):
+        n = pta.psrs[p].toas.size
+        sl = [(a, a + 4) for a in range(0, n - 40, 4)] + [(n - 30, n - 21)]
+        jv = rng.uniform(0.3, 3.0, len(sl)) * 1e-13
+        blocks.append((pta.Nvecs[p], sl, jv))
+        U = np.zeros((n, len(sl)))
+        for e, (a, b) in enumerate(sl):
+            U[a:b, e] = 1.0
+        Te = np.concatenate((pta.Ts[p], U), axis=1)
+        Text.append(Te)
+        LDt = np.longdouble
+        sig = (Te.astype(LDt).T @ (Te.astype(LDt) / pta.Nvecs[p].astype(LDt)[:, None])
+               + np.diag(1 / np.concatenate((pta.phis[p], jv)).astype(LDt)))
+        sig_ext.append(sig)
+        phiinvs.append(1.0 / pta.phis[p])
+    freqs = np.concatenate((synth.fp_freqs(7), np.array([1.0, 2.5]) / pta.Tspan))
+    tb, cb = truth.fp_sweep_truth_blockn(freqs, pta.toas, pta.residuals, blocks, pta.Ts, phiinvs)
+    tg, cg = truth.fp_sweep_truth(freqs, pta.toas, pta.residuals, pta.Nvecs, Text, sig_ext)
+    # two longdouble evaluations of one quantity: they agree to a small multiple of the LONGDOUBLE rounding
+    # times the conditioning figure (which is in units of the relative rounding error)
+    eps_ld = float(np.finfo(np.longdouble).eps)
+    assert np.all(np.abs((tb - tg).astype(float)) <= 1e-14 * np.abs(tg.astype(float)) + 1e4 * eps_ld * np.maximum(cb, cg))
