@@ -206,3 +206,36 @@ def test_pack_from_device_built_sigmas_matches_goldens(golden):
     ora_terms = o.fp_sweep(g["freqs"], g.lst("toas"), g.lst("res"), Nvecs, Ts, sigmas, per_pulsar=True)
     tol = term_tolerance(g["truth_terms"], g["cond"], ora_terms)
     assert np.all(np.abs(got - g["ref_fp"]) <= 1e-10 * np.abs(g["ref_fp"]) + 4 * tol.sum(0))
+
+
+def test_in_place_edit_of_the_inputs_rebuilds_the_pack():
+    """the reference is a pure function of its arguments; an in-place change of ANY entry of the
+    lists must be seen (the cache key hashes every byte), not answered from a stale device pack."""
+    pta = synth.make_pta(2, [500, 700], n_tm=6, ncomps=10, seed=2)
+    f = synth.fp_freqs(40)
+    fp = fastfp_b200.FastFp(pta.psrs)
+    a = (pta.Nvecs, pta.Ts, pta.sigmas)
+    base = fp(f, *a)
+    np.testing.assert_array_equal(fp(f, *a), base)
+    pta.Nvecs[1][123] *= 1.5  # one TOA re-weighted in place: misses any sparse content sample
+    pta.sigmas[1][:] = pta.Ts[1].T @ (pta.Ts[1] / pta.Nvecs[1][:, None]) + np.diag(1.0 / pta.phis[1])
+    edited = fp(f, *a)
+    fresh = fastfp_b200.FastFp(pta.psrs)(f, *a)
+    np.testing.assert_array_equal(edited, fresh)
+    assert np.abs(edited / base - 1).max() > 1e-6
+    fp.invalidate()
+    np.testing.assert_array_equal(fp(f, *a), fresh)
+    np.testing.assert_array_equal(fp.prepare(*a, force=True).fp_sweep(f), fresh)
+
+
+def test_non_spd_sigma_is_reported_and_propagates_nan():
+    """the sweep path factorises Sigma = L L^T; a Sigma that is not numerically SPD gives NaN for
+    that pulsar (like a singular Sigma in the reference) and the pack says which pulsar and pivot."""
+    pta = synth.make_pta(2, [300, 300], n_tm=4, ncomps=5, seed=6)
+    bad = [pta.sigmas[0], pta.sigmas[1].copy()]
+    bad[1][3, 3] = -abs(bad[1][3, 3])
+    fp = fastfp_b200.FastFp(pta.psrs)
+    with pytest.warns(RuntimeWarning, match=r"pulsar\(s\) 1 \(pivot 3\)"):
+        out = fp.per_pulsar_terms(synth.fp_freqs(5), pta.Nvecs, pta.Ts, bad)
+    assert np.all(np.isfinite(out[0])) and np.all(np.isnan(out[1]))
+    assert fp.prepare(pta.Nvecs, pta.Ts, bad).factor_info() == [0, 4]
