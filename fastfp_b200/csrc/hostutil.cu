@@ -50,7 +50,7 @@ extern "C" uint64_t fastfp_hash64(const void* data, int64_t nbytes, uint64_t see
     }
   };
   unsigned nt = std::thread::hardware_concurrency();
-  nt = nt > 8 ? 8 : (nt < 1 ? 1 : nt);
+  nt = nt > 16 ? 16 : (nt < 1 ? 1 : nt);
   if (nblk < 4 || nt == 1) {
     work(0, nblk);
   } else {

@@ -39,11 +39,82 @@ def _fingerprint(lists) -> tuple:
     return tuple(key)
 
 
+def _shape_key(lists) -> tuple:
+    """Cheap structural key (lengths and shapes only): decides whether the cached pack can even be tried."""
+    key = []
+    for lst in lists:
+        key.append(len(lst))
+        for a in lst:
+            key.append((np.shape(a._nvec), len(a._slices)) if hasattr(a, "_nvec") else np.shape(a))
+    return tuple(key)
+
+
+_HASHER = None
+
+
+def _hasher():
+    """One worker thread for the content hash (the ctypes calls release the GIL)."""
+    global _HASHER
+    if _HASHER is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _HASHER = ThreadPoolExecutor(max_workers=1, thread_name_prefix="fastfp-hash")
+    return _HASHER
+
+
+class _PackCache:
+    """The device pack is a CACHE of the caller's lists; the reference is a pure function of them. Every call
+    hashes every byte of the lists. To keep that off the critical path the sweep is started on the cached pack
+    right away while the hash runs on a worker thread (or, for asynchronous device-resident calls, on this thread
+    after the launch); if the hash shows the inputs changed, the pack is rebuilt and the sweep repeated -- the
+    caller never sees a result computed from stale data."""
+
+    _pack = None
+    _pack_key = None
+    _pack_shape = None
+
+    def invalidate(self):
+        """Drop the cached device pack (the next call rebuilds it)."""
+        if self._pack is not None:
+            self._pack.close()
+        self._pack, self._pack_key, self._pack_shape = None, None, None
+
+    def _build_pack(self, lists):  # -> _cabi.Pack
+        raise NotImplementedError
+
+    def _ensure(self, lists, force=False, key=None):
+        key = _fingerprint(lists) if key is None else key
+        if force or self._pack is None or key != self._pack_key:
+            if self._pack is not None:
+                self._pack.close()
+                self._pack = None
+            self._pack = self._build_pack(lists)
+            self._pack_key, self._pack_shape = key, _shape_key(lists)
+        return self._pack
+
+    def _run_verified(self, lists, run, asynchronous):
+        """``run(pack)`` on a pack that is verified to match ``lists`` byte for byte."""
+        if self._pack is None or _shape_key(lists) != self._pack_shape:
+            return run(self._ensure(lists))
+        if asynchronous:  # the launch returns at once: hash here while the GPU works
+            res = run(self._pack)
+            key = _fingerprint(lists)
+        else:             # the call blocks until the result is on the host: hash on the worker meanwhile
+            fut = _hasher().submit(_fingerprint, lists)
+            try:
+                res = run(self._pack)
+            finally:
+                key = fut.result()
+        if key == self._pack_key:
+            return res
+        return run(self._ensure(lists, key=key))  # the inputs changed: rebuild, repeat
+
+
 def _is_cuda_tensor(x) -> bool:
     return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
 
 
-class FastFp(object):
+class FastFp(_PackCache):
     """Fp-statistic (Ellis, Siemens & Creighton 2012) for a list of pulsars.
 
     :param psrs: objects with ``.toas`` and ``.residuals`` (seconds) -- all the reference reads
@@ -62,32 +133,21 @@ class FastFp(object):
 
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = int(device)
-        self._pack = None
-        self._pack_key = None
 
     # -- packing (one-time, frequency-independent precompute on the device) -----------------
-    def invalidate(self):
-        """Drop the cached device pack (the next call rebuilds it)."""
-        if self._pack is not None:
-            self._pack.close()
-        self._pack, self._pack_key = None, None
+    def _build_pack(self, lists):
+        from . import blockn
+
+        Nvecs, Ts, sigmas = lists
+        if any(blockn.is_block(N) for N in Nvecs):  # block-diagonal N (kernel ECORR)
+            return _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
+        return _cabi.Pack.create_fp(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
 
     def prepare(self, Nvecs, Ts, sigmas, force=False):
         """Upload and pre-reduce the per-pulsar arrays. The pack is cached and keyed on the full contents
         of the three lists (every byte is hashed on each call), so passing different arrays -- or the same
         arrays edited in place -- rebuilds it; ``force=True`` rebuilds unconditionally."""
-        key = _fingerprint((Nvecs, Ts, sigmas))
-        if force or self._pack is None or key != self._pack_key:
-            if self._pack is not None:
-                self._pack.close()
-            from . import blockn
-
-            if any(blockn.is_block(N) for N in Nvecs):  # block-diagonal N (kernel ECORR)
-                self._pack = _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
-            else:
-                self._pack = _cabi.Pack.create_fp(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
-            self._pack_key = key
-        return self._pack
+        return self._ensure((Nvecs, Ts, sigmas), force=force)
 
     def __call__(self, fgw, Nvecs, Ts, sigmas):
         """Callable method (reference ``fastfp.py:47-49``)."""
@@ -96,7 +156,7 @@ class FastFp(object):
     def calculate_Fp(self, fgw, Nvecs, Ts, sigmas):
         """Fp at ``fgw`` (reference ``fastfp.py:51-92``); see the module docstring for the
         batched forms of ``fgw``."""
-        pack = self.prepare(Nvecs, Ts, sigmas)
+        lists = (Nvecs, Ts, sigmas)
         if _is_cuda_tensor(fgw):
             import torch
 
@@ -107,10 +167,14 @@ class FastFp(object):
             f = fgw.contiguous().reshape(-1)
             out = torch.empty(f.shape[0], dtype=torch.float64, device=f.device)
             stream = torch.cuda.current_stream(f.device).cuda_stream
-            pack.fp_sweep((f.data_ptr(), f.shape[0]), out=out.data_ptr(), stream=stream)
-            return out.reshape(fgw.shape)
+
+            def run(pack):
+                pack.fp_sweep((f.data_ptr(), f.shape[0]), out=out.data_ptr(), stream=stream)
+                return out
+
+            return self._run_verified(lists, run, asynchronous=True).reshape(fgw.shape)
         f = np.asarray(fgw, dtype=np.float64)
-        res = pack.fp_sweep(f.reshape(-1))
+        res = self._run_verified(lists, lambda pack: pack.fp_sweep(f.reshape(-1)), asynchronous=False)
         return np.float64(res[0]) if f.ndim == 0 else res.reshape(f.shape)
 
     compute_Fp = calculate_Fp

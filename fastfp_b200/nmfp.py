@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _cabi
 from . import constants as const
-from .fastfp import _fingerprint, _is_cuda_tensor
+from .fastfp import _PackCache, _is_cuda_tensor
 
 
 def _powerlaw(Ffreqs, log10_A, gamma):
@@ -199,7 +199,7 @@ class RN_container(object):
         return cls(psr, Ffreqs, ncomps, gp_ecorr, ecorr_container, add_curn, curn_container)
 
 
-class NMFP(object):
+class NMFP(_PackCache):
     """Noise-marginalised Fp-statistic (reference ``nmfp.py:22-128``).
 
     :param psrs: objects with ``.toas`` / ``.residuals`` (``nmfp.py:50-51``)
@@ -212,8 +212,6 @@ class NMFP(object):
         self.toas = [np.asarray(psr.toas, dtype=np.float64) for psr in psrs]
         self.residuals = [np.asarray(psr.residuals, dtype=np.float64) for psr in psrs]
         self.device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
-        self._pack = None
-        self._pack_key = None
 
     def __call__(self, fgw, samples, Nvecs, Ts, TNTs):
         return self.calculate_nmfp(fgw, samples, Nvecs, Ts, TNTs)
@@ -227,36 +225,27 @@ class NMFP(object):
             sigmas.append(np.asarray(TNT, dtype=np.float64) + np.diag(phiinv))
         return sigmas
 
-    def invalidate(self):
-        """Drop the cached device pack (the next call rebuilds it)."""
-        if self._pack is not None:
-            self._pack.close()
-        self._pack, self._pack_key = None, None
-
     def prepare(self, Nvecs, Ts, TNTs, force=False):
         """Cached like :meth:`FastFp.prepare`: keyed on a hash of every byte of the three lists."""
-        key = _fingerprint((Nvecs, Ts, TNTs))
-        if force or self._pack is None or key != self._pack_key:
-            if self._pack is not None:
-                self._pack.close()
-            fixed = [sig.fixed_phi() for sig in self.rn_sigs]
-            m_fix = [f.shape[0] for f in fixed]
-            for p, (sig, T) in enumerate(zip(self.rn_sigs, Ts)):
-                if m_fix[p] + sig.Ffreqs.shape[0] != np.shape(T)[1]:
-                    raise ValueError(
-                        f"pulsar {p}: basis has {np.shape(T)[1]} columns but the RN_container describes "
-                        f"{m_fix[p]} fixed + {sig.Ffreqs.shape[0]} red-noise entries"
-                    )
-            from . import blockn
+        return self._ensure((Nvecs, Ts, TNTs), force=force)
 
-            if any(blockn.is_block(N) for N in Nvecs):  # block-diagonal N (kernel ECORR)
-                self._pack = _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
-                                                      [1.0 / f for f in fixed], device=self.device)
-            else:
-                self._pack = _cabi.Pack.create_nmfp(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
-                                                    [1.0 / f for f in fixed], device=self.device)
-            self._pack_key = key
-        return self._pack
+    def _build_pack(self, lists):
+        from . import blockn
+
+        Nvecs, Ts, TNTs = lists
+        fixed = [sig.fixed_phi() for sig in self.rn_sigs]
+        m_fix = [f.shape[0] for f in fixed]
+        for p, (sig, T) in enumerate(zip(self.rn_sigs, Ts)):
+            if m_fix[p] + sig.Ffreqs.shape[0] != np.shape(T)[1]:
+                raise ValueError(
+                    f"pulsar {p}: basis has {np.shape(T)[1]} columns but the RN_container describes "
+                    f"{m_fix[p]} fixed + {sig.Ffreqs.shape[0]} red-noise entries"
+                )
+        if any(blockn.is_block(N) for N in Nvecs):  # block-diagonal N (kernel ECORR)
+            return _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
+                                            [1.0 / f for f in fixed], device=self.device)
+        return _cabi.Pack.create_nmfp(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
+                                      [1.0 / f for f in fixed], device=self.device)
 
     def _curn_setup(self):
         flags = {bool(sig.add_curn) for sig in self.rn_sigs}
@@ -276,7 +265,7 @@ class NMFP(object):
         """Fp at ``fgw`` for the noise parameters ``samples`` (reference ``nmfp.py:76-119``)."""
         import torch
 
-        pack = self.prepare(Nvecs, Ts, TNTs)
+        lists = (Nvecs, Ts, TNTs)
         P = len(self.rn_sigs)
         curn = self._curn_setup()
         names = [(s.rn_A_name, s.rn_gam_name) for s in self.rn_sigs]
@@ -294,20 +283,29 @@ class NMFP(object):
 
         dev = torch.device("cuda", self.device)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        phiinv = torch.empty((D, pack.mvar_total), dtype=torch.float64, device=dev)
-        pack.powerlaw_phiinv([s.Ffreqs for s in self.rn_sigs], A, G, None if curn is None else curn.Ffreqs,
-                             cA, cG, phiinv.data_ptr(), stream=stream)
-        if _is_cuda_tensor(fgw):
+        on_dev = _is_cuda_tensor(fgw)
+        if on_dev:
             if fgw.dtype != torch.float64:
                 raise TypeError("fgw tensor must be float64")
             if fgw.device.index != self.device:
                 raise ValueError(f"fgw is on {fgw.device}, the pack on cuda:{self.device}")
             f = fgw.contiguous().reshape(-1)
             out = torch.empty((D, f.shape[0]), dtype=torch.float64, device=dev)
-            pack.nmfp_sweep((f.data_ptr(), f.shape[0]), phiinv.data_ptr(), D, out=out.data_ptr(), stream=stream)
-            return out if batched else out[0]
-        f = np.asarray(fgw, dtype=np.float64)
-        res = pack.nmfp_sweep(f.reshape(-1), phiinv.data_ptr(), D, stream=stream)  # (D, F) on the host
+        else:
+            f = np.asarray(fgw, dtype=np.float64)
+
+        def run(pack):
+            phiinv = torch.empty((D, pack.mvar_total), dtype=torch.float64, device=dev)
+            pack.powerlaw_phiinv([s.Ffreqs for s in self.rn_sigs], A, G, None if curn is None else curn.Ffreqs,
+                                 cA, cG, phiinv.data_ptr(), stream=stream)
+            if on_dev:
+                pack.nmfp_sweep((f.data_ptr(), f.shape[0]), phiinv.data_ptr(), D, out=out.data_ptr(), stream=stream)
+                return out
+            return pack.nmfp_sweep(f.reshape(-1), phiinv.data_ptr(), D, stream=stream)  # (D, F) on the host
+
+        res = self._run_verified(lists, run, asynchronous=on_dev)
+        if on_dev:
+            return res if batched else res[0]
         if f.ndim == 0:
             res = res[:, 0]
         if not batched:
