@@ -5,9 +5,9 @@
 Two ways to get the inputs:
   * ``--synthetic P N``: seeded synthetic pulsars (no ``enterprise`` needed);
   * ``psrfile noisefile``: a pickle of ``enterprise`` pulsars and a noise JSON, exactly as the
-    reference script takes them -- model construction then uses the reference's own
-    ``fastfp.utils.initialize_pta`` (needs ``enterprise``/``fastfp`` installed), only the hot path
-    is swapped: ``FastFp``, ``get_mats_fp`` and ``vmap`` come from ``fastfp_b200``.
+    reference script takes them -- model construction goes through ``fastfp_b200.utils.initialize_pta``
+    (a pass-through to ``enterprise``, which must be installed); ``FastFp``, ``get_mats_fp`` and ``vmap``
+    come from ``fastfp_b200``.
 """
 import argparse
 import json
@@ -32,7 +32,7 @@ def main(psrfile=None, noisefile=None, savefile="fp_out", synthetic=None, nfreqs
         pta = synth.make_pta(synthetic[0], synthetic[1])
         psrs, noise = pta.psrs, pta.noise
     else:
-        from fastfp.utils import initialize_pta  # reference model construction (enterprise)
+        from fastfp_b200.utils import initialize_pta  # pass-through to enterprise (must be installed)
 
         with open(psrfile, "rb") as f:
             psrs = pickle.load(f)
@@ -66,4 +66,11 @@ if __name__ == "__main__":
     parser.add_argument("savefile", nargs="?", default="fp_out", type=str, help="filename for resulting Fp dictionary")
     parser.add_argument("--synthetic", nargs=2, type=int, metavar=("P", "NTOA"), help="use synthetic pulsars")
     parser.add_argument("--nfreqs", type=int, default=200)
-    main(**vars(parser.parse_args()))
+    parser.add_argument("--save", type=str, default=None, help="output name (alternative to the positional savefile)")
+    kwargs = vars(parser.parse_args())
+    save = kwargs.pop("save")
+    if save:
+        kwargs["savefile"] = save
+    if not kwargs["synthetic"] and not (kwargs["psrfile"] and kwargs["noisefile"]):
+        parser.error("give psrfile noisefile [savefile], or --synthetic P NTOA")
+    main(**kwargs)

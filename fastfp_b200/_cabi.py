@@ -59,6 +59,8 @@ SYMBOLS = {
     "fastfp_pack_bytes": (C.c_int64, [C.c_void_p]),
     "fastfp_pack_num_pulsars": (C.c_int, [C.c_void_p]),
     "fastfp_pack_mvar_total": (C.c_int64, [C.c_void_p]),
+    "fastfp_pack_set_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "fastfp_pack_path": (C.c_int, [C.c_void_p]),
     "fastfp_pack_factor_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "fastfp_hash64": (C.c_uint64, [C.c_void_p, C.c_int64, C.c_uint64]),
     "fastfp_kernel_launches": (C.c_int64, []),
@@ -179,6 +181,17 @@ class Pack:
         self._h, self.P, self.device, self.nmfp = handle, P, device, nmfp
         self.n, self.m = list(n), list(m)
         self._warn_if_not_spd()
+
+    PATHS = {"auto": 0, "fp64": 1, "i8": 2}
+
+    def set_path(self, path: str) -> None:
+        """Kernel of the plain-Fp sweep: "auto" (default: the INT8 tensor-core kernel when the pack has digit
+        planes), "fp64" (the DMMA kernel) or "i8" (raises if the pack cannot take it)."""
+        check(load().fastfp_pack_set_path(self._h, self.PATHS[path]))
+
+    @property
+    def path(self) -> str:
+        return {1: "fp64", 2: "i8"}[load().fastfp_pack_path(self._h)]
 
     def factor_info(self):
         """Per-pulsar status of the one-time Cholesky (0 = fine, j+1 = pivot j not positive)."""

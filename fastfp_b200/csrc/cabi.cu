@@ -168,6 +168,7 @@ static void pack_free(fastfp_pack* pk) {
   cudaFree(pk->d_S0); cudaFree(pk->d_zr); cudaFree(pk->d_slab); cudaFree(pk->d_counter); cudaFree(pk->d_done_mask);
   cudaFree(pk->d_terms); cudaFree(pk->d_freqs); cudaFree(pk->d_out); cudaFree(pk->d_scratch);
   cudaFree(pk->d_pl); cudaFreeHost(pk->h_pl);
+  cudaFree(pk->d_i8); cudaFree(pk->d_i8_scale); cudaFree(pk->d_pidx_all);
   if (pk->pl_event) cudaEventDestroy(pk->pl_event);
   delete pk;
 }
@@ -209,9 +210,30 @@ int fastfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
   if (!rc) rc = upload_ragged(&sg.d_T, Ts, pk, 1, st);
   if (!rc) rc = upload_ragged(&pk->d_L, sigmas, pk, 2, st);
   if (!rc) rc = launch_fp_precompute(pk, sg.d_toas, sg.d_res, sg.d_Nvec, sg.d_T, st);
+  if (!rc) rc = build_i8_planes(pk, st);  // digit planes for the tensor path when every pulsar fits its tile
   if (rc) { pack_free(pk); return rc; }
   *out = pk;
   return FASTFP_OK;
+}
+
+int fastfp_pack_set_path(fastfp_pack_t* pk, int path) {
+  if (!pk || path < FASTFP_PATH_AUTO || path > FASTFP_PATH_I8) {
+    set_error("fastfp_pack_set_path: invalid argument");
+    return FASTFP_ERR_INVALID;
+  }
+  if (path == FASTFP_PATH_I8 && !pk->i8_ok) {
+    set_error("fastfp_pack_set_path: this pack has no INT8 digit planes (block-diagonal N, nmfp, m > 127, "
+              "n > 16384 or non-finite data)");
+    return FASTFP_ERR_UNSUPPORTED;
+  }
+  pk->path = path;
+  return FASTFP_OK;
+}
+
+int fastfp_pack_path(const fastfp_pack_t* pk) {
+  if (!pk) return FASTFP_ERR_INVALID;
+  if (pk->path == FASTFP_PATH_AUTO) return pk->i8_ok ? FASTFP_PATH_I8 : FASTFP_PATH_FP64;
+  return pk->path;
 }
 
 int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
@@ -347,6 +369,12 @@ int fastfp_pack_factor_info(const fastfp_pack_t* pack, int32_t* info) {
 // Frequencies are processed in batches so the (P, F_batch) term buffer stays bounded.
 static const int64_t kTermBudgetDoubles = 1LL << 27;  // 1 GiB
 
+// per-pulsar terms of one frequency batch on the path the pack is set to
+static int sweep_terms(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st) {
+  const bool i8 = pk->i8_ok && pk->path != FASTFP_PATH_FP64;
+  return i8 ? launch_fp_sweep_i8(pk, d_freqs, F, d_terms, st) : launch_fp_sweep(pk, d_freqs, F, d_terms, st);
+}
+
 static int fp_run(const fastfp_pack* pk, const double* freqs, int64_t F, double* out, int flags,
                   void* stream, bool want_terms) {
   if (!pk || (F > 0 && (!freqs || !out)) || F < 0) {
@@ -371,7 +399,7 @@ static int fp_run(const fastfp_pack* pk, const double* freqs, int64_t F, double*
       if (int rc = ensure(&pk->d_terms, &pk->terms_cap, (int64_t)P * F)) return rc;
       d_terms = pk->d_terms;
     }
-    if (int rc = launch_fp_sweep(pk, d_freqs, F, d_terms, st)) return rc;
+    if (int rc = sweep_terms(pk, d_freqs, F, d_terms, st)) return rc;
     if (!odev) {
       FFP_CUDA(cudaMemcpyAsync(out, d_terms, (size_t)P * F * 8, cudaMemcpyDeviceToHost, st));
       FFP_CUDA(cudaStreamSynchronize(st));
@@ -387,7 +415,7 @@ static int fp_run(const fastfp_pack* pk, const double* freqs, int64_t F, double*
   if (int rc = ensure(&pk->d_terms, &pk->terms_cap, (int64_t)P * std::min(FB, F))) return rc;
   for (int64_t lo = 0; lo < F; lo += FB) {
     const int64_t fb = std::min(FB, F - lo);
-    if (int rc = launch_fp_sweep(pk, d_freqs + lo, fb, pk->d_terms, st)) return rc;
+    if (int rc = sweep_terms(pk, d_freqs + lo, fb, pk->d_terms, st)) return rc;
     if (int rc = launch_reduce_terms(pk->d_terms, P, fb, d_out + lo, st)) return rc;
   }
   if (!odev) {

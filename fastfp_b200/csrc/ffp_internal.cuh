@@ -89,6 +89,9 @@ struct PulsarMeta {
   int32_t ci;          // TOAs per packet for this pulsar's kernel configuration
   double tabs_max;     // max |TOA| (inf if any TOA is not finite): decides the sincos path per tile
   int64_t dm_off;      // block-N packs: offset of this pulsar's per-chunk slot masks
+  int64_t i8_off;      // tensor path: byte offset of this pulsar's digit-plane stages
+  int32_t i8_rows;     // tensor path: rows stored per plane (basis rows + the w row, padded to 8)
+  int32_t i8_nst;      // tensor path: stages of 32 TOAs
 };
 
 struct KernelCfg {  // run-time mirror of SweepCfg's parameters
@@ -130,6 +133,14 @@ struct fastfp_pack {
   std::vector<int> info;        // host copy, read back when the pack is built (fastfp_pack_factor_info)
   double* d_slab = nullptr;     // level-2 accumulation scratch, one slab per resident CTA
   unsigned int* d_counter = nullptr;  // persistent-CTA work counter
+  // INT8 tensor-core path (fp_sweep_i8.cu): digit planes of G, per-row scales; chosen per pack
+  unsigned char* d_i8 = nullptr;
+  double* d_i8_scale = nullptr;   // [P][128]
+  int* d_pidx_all = nullptr;      // identity pulsar list
+  bool i8_ok = false;             // the planes exist (every pulsar fits the tile, all values finite)
+  int i8_rows_max = 0;
+  int64_t i8_bytes = 0;
+  int path = 0;                   // FASTFP_PATH_AUTO / _FP64 / _I8 (fastfp_pack_set_path)
   int64_t bytes = 0;
   int64_t mvar_total = 0;
   int mvar_max = 0;
@@ -190,6 +201,10 @@ struct NmfpOut {      // stage-A outputs of the nmfp path (null for plain Fp)
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
                     cudaStream_t st, const NmfpOut* nm = nullptr);
 int launch_reduce_terms(const double* d_terms, int P, int64_t F, double* d_out, cudaStream_t st);
+// fp_sweep_i8.cu
+bool i8_eligible(const fastfp_pack* pk);
+int build_i8_planes(fastfp_pack* pk, cudaStream_t st);
+int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st);
 bool sweep_config(int m, KernelCfg* cfg);
 int sweep_max_slab_doubles();
 // xcy.cu

@@ -1,0 +1,654 @@
+// The frequency-sweep kernel on the 5th-generation tensor cores: Y = G [s c] as an error-free product of 8-bit
+// digit planes (tcgen05.mma kind::i8, exact int32 accumulation in tensor memory), everything else in fp64.
+//
+// Replaces the body of FastFp.calculate_Fp under jax.vmap (reference fastfp/fastfp.py:69-92, examples/run_fp.py:63)
+// like fp_sweep_kernel.cuh does, for packs whose pulsars fit the tile (basis width m <= 127, n <= 16384 TOAs, diagonal
+// N); the fp64 DMMA kernel stays as the path for everything else. Why: fp64 has no tcgen05 kind, and the DMMA
+// formulation is pinned at 0.68 of the fp64 pipe it has to share with the sincos generation.
+// The INT8 tensor path is a different unit altogether, and integer accumulation is exact.
+//
+// Number format (radix 256, 7 planes per operand, validated at the level of the statistic by
+// tests/test_split_precision_emulation.py):
+//   G row j (and the extra row w = C^-1 r):  g = G / 2^e_j with |g| < 1/4,  Qg = rint(g 2^55),
+//        Qg = sum_i d_i 256^(6-i), balanced digits d_i in [-128, 127]  (pack time, i8_planes_kernel)
+//   s, c in [-1, 1]:  Q = rint(x 2^54) = sum_j v_j 256^(6-j), balanced digits (producers: two magic-constant
+//        roundings give the high 26 and the low 28 bits as integers, the bytes of Q + 0x80..80 are the digits + 128)
+//   Y_j = 2^(e_j - 13) sum_{g=0..6} 256^-g  sum_{i+j=g} sum_k d_i(k) v_j(k):   28 plane products, one int32
+//        accumulator per weight g (|d v| <= 2^14, 7 products per TOA: exact for n <= 18 724 TOAs)
+//
+// One 768-thread CTA per SM, static round-robin over (pulsar, 32-frequency tile) work items, per stage of 32 TOAs:
+//   warp 0   lane 0: TMA -- one bulk copy of the stage's G planes (7 x rows x 32 bytes, already in the SWIZZLE_32B
+//            K-major operand layout) and one of its (t, 1/N) vectors, mbarrier rings
+//   warp 1   lane 0: 28 tcgen05.mma (M = 128: rows of G, N = 64: 32 frequencies x {sin, cos}, K = 32 TOAs) into the
+//            7 accumulators (7 x 64 = 448 of the 512 TMEM columns); tcgen05.commit frees the stage
+//   warps 8-23 (producers, two groups alternating stages): sincos_cw of ((2 pi) f) t (fastfp.py:78-79 phase order),
+//            the digit split, 14 conflict-free 4-byte stores per thread into the B-operand planes, and the three
+//            fp64 sums s N^-1 s, s N^-1 c, c N^-1 c
+//   warps 4-7 (epilogue, one TMEM lane quarter each): tcgen05.ld, fp64 recombination, b = Y_s.Y_s, Y_s.Y_c, Y_c.Y_c
+//            over the basis rows, (s|r), (c|r) from the w row, pivoted 2x2 solve (jnp.linalg.solve at fastfp.py:90)
+// Shared memory is the bound: an M=128, N=64 MMA reads 6 KB of operands, 48 cycles at 128 B/clk (measured,
+// tools/probes/umma_i8_shape_probe.cu), i.e. 1344 cycles per stage against ~3490 for the same work on the DMMA path.
+#include <cmath>
+#include <cstdio>
+
+#include "../../include/fastfp_b200.h"
+#include "ffp_internal.cuh"
+#include "ffp_sincos.cuh"
+
+namespace ffp {
+namespace i8 {
+
+constexpr int NPL = 7;                 // digit planes per operand
+constexpr int KT = 32;                 // TOAs per stage = K bytes per operand row (one SWIZZLE_32B atom wide)
+constexpr int NF = 32;                 // frequencies per work item
+constexpr int NBR = 2 * NF;            // rows of the B operand: row = 32 * {0: sin, 1: cos} + frequency
+constexpr int S_PLANE = NBR * KT;      // 2048 bytes
+constexpr int S_STAGE = NPL * S_PLANE; // 14336 bytes
+constexpr int V_STAGE = KT * 16;       // (t, 1/N) per TOA
+constexpr int SST = 6, VST = 8;        // ring depths (even: a slot is always served by the same producer group)
+constexpr int THREADS = 768;
+constexpr int NPW = 16;                // producer warps
+constexpr int REGS_LAUNCH = 80, REGS_CTRL = 40, REGS_EPI = 144, REGS_PROD = 72;
+static_assert(128 * REGS_CTRL + 128 * REGS_EPI + 512 * REGS_PROD <= THREADS * REGS_LAUNCH, "register pool");
+static_assert(SST % 2 == 0 && VST % 2 == 0, "ring depths must be even");
+
+struct Args {
+  const unsigned char* planes;   // per pulsar, per stage: [V_STAGE bytes (t, 1/N)][NPL][rows][32] swizzled
+  const double* rowscale;        // [P][128]  2^(e_j - 13), 0 for rows that do not exist
+  const PulsarMeta* meta;
+  const int* pidx;
+  const double* freqs;
+  int64_t F;
+  double* terms;                 // [P][F]
+  int ntile, nwork;
+  int gslot, gst;                // G ring: bytes per slot (7 x rows_max x 32), number of slots
+};
+
+// byte offset of (row r, K byte c) in a K-major tile with 32-byte rows, SWIZZLE_32B: 8-row groups of 256 bytes, the
+// 16-byte chunk index XORed with bit 2 of the row (validated by tools/probes/umma_i8_split_check.cu)
+__host__ __device__ inline int swz32(int r, int c) {
+  return (r >> 3) * 256 + (r & 7) * 32 + ((((c >> 4) ^ ((r & 7) >> 2)) & 1) << 4) + (c & 15);
+}
+
+// ---- pack time: digit planes of G (+ the w row) --------------------------------------------------------------
+// e_j from the row maximum: |G_j / 2^e_j| < 1/4; rs_j = 2^(e_j - 13). bad[p] is set when a row holds a non-finite
+// value (singular Sigma, NaN data): the integer planes could not carry it, so such a pack stays on the fp64 path.
+__global__ void i8_rowscale_kernel(const double* __restrict__ packets, const PulsarMeta* __restrict__ meta,
+                                   double* __restrict__ rowscale, int* __restrict__ rowexp, int* __restrict__ bad) {
+  const PulsarMeta pm = meta[blockIdx.y];
+  const int r = blockIdx.x;
+  if (r >= 128) return;
+  double* rs = rowscale + (size_t)blockIdx.y * 128 + r;
+  int* re = rowexp + (size_t)blockIdx.y * 128 + r;
+  if (r > pm.m) {
+    if (threadIdx.x == 0) { *rs = 0.0; *re = 0; }
+    return;
+  }
+  const int CI = pm.ci, mp = pm.mpad, pkw = CI * (4 + mp);
+  const double* pk0 = packets + pm.pk_off;
+  double mx = 0.0;
+  bool nonfinite = false;
+  for (int i = threadIdx.x; i < pm.n; i += blockDim.x) {
+    const double* pk = pk0 + (size_t)(i / CI) * pkw;
+    const int il = i % CI;
+    const double v = r < pm.m ? pk[4 * CI + g_frag_index(il, r, mp >> 3)] : pk[4 * il + 2];  // G row or w
+    const double a = fabs(v);
+    if (!(a <= 1.7e308)) nonfinite = true;
+    mx = fmax(mx, a);
+  }
+  __shared__ double smx[32];
+  __shared__ int snf;
+  if (threadIdx.x == 0) snf = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+  if (nonfinite) atomicOr(&snf, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, smx[w]);
+    int e = 0;
+    if (mx > 0.0) {
+      int x;
+      frexp(mx, &x);  // mx = f 2^x, f in [1/2, 1)  ->  |G| < 2^x
+      e = x + 2;
+    }
+    *re = e;
+    *rs = mx > 0.0 ? scalbn(1.0, e - 13) : 0.0;
+    if (snf) atomicOr(&bad[blockIdx.y], 1);
+  }
+}
+
+// one CTA per (stage, pulsar): the (t, 1/N) vectors and the 7 x rows x 32 digit bytes of the stage
+__global__ void i8_planes_kernel(const double* __restrict__ packets, const PulsarMeta* __restrict__ meta,
+                                 const int* __restrict__ rowexp, unsigned char* __restrict__ planes) {
+  const PulsarMeta pm = meta[blockIdx.y];
+  const int st = blockIdx.x;
+  if (st >= pm.i8_nst) return;
+  const int rows = pm.i8_rows, CI = pm.ci, mp = pm.mpad, pkw = CI * (4 + mp);
+  const double* pk0 = packets + pm.pk_off;
+  unsigned char* out = planes + pm.i8_off + (size_t)st * (V_STAGE + NPL * rows * KT);
+  double2* v = reinterpret_cast<double2*>(out);
+  for (int kk = threadIdx.x; kk < KT; kk += blockDim.x) {
+    const int i = st * KT + kk;
+    double2 tv = make_double2(0.0, 0.0);  // padded TOAs: weight 0 (and zero digits below)
+    if (i < pm.n) {
+      const double* pk = pk0 + (size_t)(i / CI) * pkw;
+      tv = make_double2(pk[4 * (i % CI)], pk[4 * (i % CI) + 1]);
+    }
+    v[kk] = tv;
+  }
+  unsigned char* g = out + V_STAGE;
+  const int* re = rowexp + (size_t)blockIdx.y * 128;
+  for (int e = threadIdx.x; e < rows * KT; e += blockDim.x) {
+    const int r = e / KT, kk = e - r * KT;
+    const int i = st * KT + kk;
+    double val = 0.0;
+    if (i < pm.n && r <= pm.m) {
+      const double* pk = pk0 + (size_t)(i / CI) * pkw;
+      const int il = i % CI;
+      val = r < pm.m ? pk[4 * CI + g_frag_index(il, r, mp >> 3)] : pk[4 * il + 2];
+    }
+    // Qg = rint(val 2^(55 - e)): exact scaling, |Qg| <= 2^53; balanced base-256 digits = bytes of Qg + 0x80..80, - 128
+    const long long Q = __double2ll_rn(scalbn(val, 55 - re[r]));
+    const unsigned long long U = (unsigned long long)(Q + 0x0080808080808080LL) ^ 0x0080808080808080ULL;
+    const int off = swz32(r, kk);
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) g[(size_t)p * rows * KT + off] = (unsigned char)(U >> (8 * (6 - p)));
+  }
+}
+
+// ---- device helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_32B (layout type 6), stride between 8-row groups 256 bytes, descriptor version 1
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)6 << 61);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];\n" ::"l"((uint64_t)smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int R>
+__device__ __forceinline__ void reg_set_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_set_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+// x in [-1, 1] -> the 7 bytes of rint(x 2^54) + 0x80..80 with every byte XORed with 0x80: balanced signed digits,
+// most significant in byte 6. Two magic-constant roundings give hi = rint(x 2^26) and lo = rint((x - hi 2^-26) 2^54)
+// as integers in the low mantissa bits; Q = hi 2^28 + lo exactly.
+__device__ __forceinline__ uint2 digits7(double x) {
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  const double t1 = fma(x, 67108864.0, MAGIC);
+  const double rem = fma(-(t1 - MAGIC), 1.0 / 67108864.0, x);
+  const double t2 = fma(rem, 18014398509481984.0, MAGIC);
+  const long long hi = (long long)__double2loint(t1);
+  const long long U = hi * 268435456LL + (__double_as_longlong(t2) - 0x4338000000000000LL) + 0x0080808080808080LL;
+  return make_uint2((uint32_t)U ^ 0x80808080u, (uint32_t)((unsigned long long)U >> 32) ^ 0x00808080u);
+}
+
+// Every wait of this kernel is bounded: a protocol error would otherwise hang the GPU. No legitimate wait is longer
+// than a few stages (microseconds); after ~2 s of polling the CTA reports where it was stuck and traps, which the
+// host sees as a launch failure instead of a hung device.
+__device__ __noinline__ void wait_timeout(int tag, uint32_t k) {
+  printf("[fastfp_b200 i8 sweep] mbarrier wait timed out: tag %d, stage/item %u, block %d, warp %d\n", tag, k,
+         (int)blockIdx.x, (int)(threadIdx.x >> 5));
+  __trap();
+}
+__device__ __forceinline__ void wait_wd(uint64_t* bar, uint32_t parity, int tag, uint32_t k, bool spin) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (!spin) __nanosleep(64);
+    if ((++n & 1023u) == 0 && clock64() - t0 > 4000000000LL) wait_timeout(tag, k);
+  }
+}
+
+__device__ __noinline__ void sincos_library(double ph, double* s, double* c) { sincos(ph, s, c); }
+
+struct Smem {
+  unsigned char *G, *S, *V;
+  double *redA;          // [2][2][NF][3] producer sums: buffer, producer group, frequency
+  double *part;          // [4][NF][3]    epilogue partial b-sums per warp
+  double *nval;          // [NF][2]       (s|r), (c|r) from the w row
+  uint64_t *g_full, *g_empty, *v_full, *v_empty, *s_full, *s_empty, *acc_full, *acc_empty, *sums_full, *sums_empty;
+  uint32_t* tmem;
+  __device__ Smem(unsigned char* raw, const Args& ar) {
+    G = raw;
+    S = G + (size_t)ar.gst * ar.gslot;
+    V = S + SST * S_STAGE;
+    redA = reinterpret_cast<double*>(V + VST * V_STAGE);
+    part = redA + 2 * 2 * NF * 3;
+    nval = part + 4 * NF * 3;
+    g_full = reinterpret_cast<uint64_t*>(nval + NF * 2);
+    g_empty = g_full + 8;
+    v_full = g_empty + 8;
+    v_empty = v_full + VST;
+    s_full = v_empty + VST;
+    s_empty = s_full + SST;
+    acc_full = s_empty + SST;
+    acc_empty = acc_full + 1;
+    sums_full = acc_empty + 1;
+    sums_empty = sums_full + 2;
+    tmem = reinterpret_cast<uint32_t*>(sums_empty + 2);
+  }
+};
+constexpr size_t SMEM_FIXED = (size_t)SST * S_STAGE + VST * V_STAGE + (2 * 2 * NF * 3 + 4 * NF * 3 + NF * 2) * 8 +
+                              (8 + 8 + 2 * VST + 2 * SST + 2 + 4) * 8 + 16;
+
+__global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem sm(smem_raw, ar);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < ar.gst; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], 1); }
+    for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], NPW / 2); }
+    for (int s = 0; s < SST; ++s) { mbar_init(&sm.s_full[s], NPW / 2); mbar_init(&sm.s_empty[s], 1); }
+    mbar_init(sm.acc_full, 1);
+    mbar_init(sm.acc_empty, 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.sums_full[b], NPW); mbar_init(&sm.sums_empty[b], 1); }
+    fence_barrier_init();
+  }
+  if (wid == 1) {  // the MMA warp owns the tensor-memory allocation (all 512 columns: one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(sm.tmem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *sm.tmem;
+
+  if (wid < 4) {
+    // ================= control warpgroup: TMA (warp 0) and MMA issue (warp 1) =================
+    reg_set_dec<REGS_CTRL>();
+    if (wid == 0 && lane == 0) {
+      uint32_t k = 0;
+      for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x) {
+        const PulsarMeta pm = ar.meta[ar.pidx[item / ar.ntile]];
+        const uint32_t gbytes = (uint32_t)(NPL * pm.i8_rows * KT);
+        const unsigned char* src = ar.planes + pm.i8_off;
+        for (int c = 0; c < pm.i8_nst; ++c, ++k) {
+          const uint32_t sv = k % VST, sg = k % (uint32_t)ar.gst;
+          if (k >= VST) wait_wd(&sm.v_empty[sv], ((k / VST) - 1) & 1u, 1, k, false);
+          mbar_expect_tx(&sm.v_full[sv], V_STAGE);
+          tma_load_1d(sm.V + sv * V_STAGE, src, V_STAGE, &sm.v_full[sv]);
+          if (k >= (uint32_t)ar.gst) wait_wd(&sm.g_empty[sg], ((k / (uint32_t)ar.gst) - 1) & 1u, 2, k, false);
+          mbar_expect_tx(&sm.g_full[sg], gbytes);
+          tma_load_1d(sm.G + (size_t)sg * ar.gslot, src + V_STAGE, gbytes, &sm.g_full[sg]);
+          src += V_STAGE + gbytes;
+        }
+      }
+    } else if (wid == 1 && lane == 0) {
+      // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NBR >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t k = 0, it = 0;
+      for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
+        const PulsarMeta pm = ar.meta[ar.pidx[item / ar.ntile]];
+        const uint32_t aplane = (uint32_t)(pm.i8_rows * KT);
+        if (it > 0) wait_wd(sm.acc_empty, (it - 1) & 1u, 3, it, true);  // the epilogue has drained the accumulators
+        for (int c = 0; c < pm.i8_nst; ++c, ++k) {
+          const uint32_t sg = k % (uint32_t)ar.gst, ss = k % SST;
+          wait_wd(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k, true);
+          wait_wd(&sm.s_full[ss], (k / SST) & 1u, 5, k, true);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sm.G + (size_t)sg * ar.gslot), b0 = smem_u32(sm.S + ss * S_STAGE);
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const uint64_t da = umma_desc(a0 + (uint32_t)i * aplane);
+#pragma unroll
+            for (int j = 0; j < NPL - i; ++j)  // accumulator i + j; its first product of an item is (0, j)
+              umma_i8(tm + (uint32_t)((i + j) * NBR), da, umma_desc(b0 + (uint32_t)j * S_PLANE), idesc,
+                      (c > 0 || i > 0) ? 1u : 0u);
+          }
+          umma_commit(&sm.g_empty[sg]);   // both arrive when the MMAs above have read their operands
+          umma_commit(&sm.s_empty[ss]);
+        }
+        umma_commit(sm.acc_full);
+      }
+    }
+  } else if (wid < 8) {
+    // ================= epilogue warpgroup: one TMEM lane quarter per warp =================
+    reg_set_inc<REGS_EPI>();
+    const int ew = wid - 4;
+    const int row = 32 * ew + lane;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
+      const int gp = item / ar.ntile, ft = item - gp * ar.ntile;
+      const int p = ar.pidx[gp];
+      const PulsarMeta pm = ar.meta[p];
+      const int64_t f0 = (int64_t)ft * NF;
+      const double rs = ar.rowscale[(size_t)p * 128 + row];
+      const bool has_rows = 32 * ew < pm.i8_rows;  // warp-uniform
+      wait_wd(sm.acc_full, it & 1u, 6, it, false);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < NF; c0 += 8) {
+        double v[24];
+        if (has_rows) {
+          const uint32_t ta = tm + ((uint32_t)(32 * ew) << 16) + (uint32_t)c0;
+          double ysv[8], ycv[8];
+          {
+            uint32_t acc[NPL][8];
+#pragma unroll
+            for (int g = 0; g < NPL; ++g) tmem_ld8(ta + (uint32_t)(g * NBR), acc[g]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              double y = (double)(int)acc[NPL - 1][q];  // smallest weight first
+#pragma unroll
+              for (int g = NPL - 2; g >= 0; --g) y = fma(y, 0.00390625, (double)(int)acc[g][q]);
+              ysv[q] = y * rs;
+            }
+          }
+          {
+            uint32_t acc[NPL][8];
+#pragma unroll
+            for (int g = 0; g < NPL; ++g) tmem_ld8(ta + (uint32_t)(g * NBR + NF), acc[g]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              double y = (double)(int)acc[NPL - 1][q];
+#pragma unroll
+              for (int g = NPL - 2; g >= 0; --g) y = fma(y, 0.00390625, (double)(int)acc[g][q]);
+              ycv[q] = y * rs;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const double ys = ysv[q], yc = ycv[q];
+            if (row == pm.m) {  // the w row: (s|r) = s.w, (c|r) = c.w  
+              sm.nval[2 * (c0 + q)] = ys;
+              sm.nval[2 * (c0 + q) + 1] = yc;
+            }
+            const bool basis = row < pm.m;
+            v[3 * q] = basis ? ys * ys : 0.0;
+            v[3 * q + 1] = basis ? ys * yc : 0.0;
+            v[3 * q + 2] = basis ? yc * yc : 0.0;
+          }
+          // transpose-reduce over the 32 rows of this warp: 24 -> 12 -> 6 -> 3 values per lane, then lanes 4q hold
+          // the three sums of frequency c0 + q
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            const bool up = lane & 16;
+            const double keep = up ? v[i + 12] : v[i], send = up ? v[i] : v[i + 12];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const bool up = lane & 8;
+            const double keep = up ? v[i + 6] : v[i], send = up ? v[i] : v[i + 6];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const bool up = lane & 4;
+            const double keep = up ? v[i + 3] : v[i], send = up ? v[i] : v[i + 3];
+            double t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            v[i] = t;
+          }
+        } else {
+          v[0] = v[1] = v[2] = 0.0;
+        }
+        if ((lane & 3) == 0) {
+          const int q = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+          double* o = sm.part + ((size_t)ew * NF + c0 + q) * 3;
+          o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.acc_empty);  // tensor memory may be overwritten by the next item
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // partial sums and the w-row values of the 4 warps are visible
+      const uint32_t buf = it & 1u;
+      if (ew == 0) {
+        wait_wd(&sm.sums_full[buf], (it >> 1) & 1u, 7, it, false);
+        const int f = lane;
+        const int64_t fidx = f0 + f;
+        double b[3] = {0, 0, 0}, a[3];
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2)
+#pragma unroll
+          for (int k2 = 0; k2 < 3; ++k2) b[k2] += sm.part[((size_t)w2 * NF + f) * 3 + k2];
+#pragma unroll
+        for (int k2 = 0; k2 < 3; ++k2)
+          a[k2] = sm.redA[((buf * 2 + 0) * NF + f) * 3 + k2] + sm.redA[((buf * 2 + 1) * NF + f) * 3 + k2];
+        const double N0 = sm.nval[2 * f], N1 = sm.nval[2 * f + 1];
+        // M = [[ss, sc],[sc, cc]], N = [n0, n1]; LU with partial pivoting
+        double m00 = a[0] - b[0], m01 = a[1] - b[1], m10 = m01, m11 = a[2] - b[2];
+        double n0 = N0, n1 = N1;
+        if (fabs(m10) > fabs(m00)) {  // row swap; the unknowns keep their order
+          double t0 = m00; m00 = m10; m10 = t0;
+          t0 = m01; m01 = m11; m11 = t0;
+          t0 = n0; n0 = n1; n1 = t0;
+        }
+        const double lq = m10 / m00;
+        const double u = m11 - lq * m01;
+        const double x1 = (n1 - lq * n0) / u;
+        const double x0 = (n0 - m01 * x1) / m00;
+        double val = 0.5 * (N0 * x0 + N1 * x1);
+        if (fidx < ar.F) {
+          if (!(ar.freqs[fidx] > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);  // f <= 0: NaN like f**(1/3)
+          ar.terms[(size_t)p * ar.F + fidx] = val;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.sums_empty[buf]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // part / nval are rewritten by the next item
+    }
+  } else {
+    // ================= producers: sin/cos digit planes + the three quadratic sums =================
+    reg_set_dec<REGS_PROD>();
+    const int pw = wid - 8;
+    const uint32_t grp = (uint32_t)(pw >> 3);          // serves the stages with (global stage index & 1) == grp
+    const int fl = lane >> 3, kg = lane & 7;
+    const int f = 4 * (pw & 7) + fl;                   // frequency inside the tile
+    const int soff = swz32(f, 4 * kg);                 // word of TOAs 4kg..4kg+3 in row f (sin); cos row: + 1024
+    uint32_t kbase = 0, it = 0;
+    for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
+      const int gp = item / ar.ntile, ft = item - gp * ar.ntile;
+      const PulsarMeta pm = ar.meta[ar.pidx[gp]];
+      const int64_t f0 = (int64_t)ft * NF;
+      const double fq = ar.freqs[f0 + f < ar.F ? f0 + f : f0];  // a short last tile repeats its first frequency
+      const double omega = __dmul_rn(6.283185307179586, fq);     // (2*pi)*f, rounded once (fastfp.py:78)
+      const bool fast = __all_sync(0xffffffffu, fabs(omega) * pm.tabs_max <= 0.999 * FFP_SINCOS_MAX);
+      double s3[3] = {0.0, 0.0, 0.0};
+      const int nst = pm.i8_nst;
+      for (int c = (int)((kbase ^ grp) & 1u); c < nst; c += 2) {
+        const uint32_t k = kbase + (uint32_t)c;
+        const uint32_t sv = k % VST, ss = k % SST;
+        wait_wd(&sm.v_full[sv], (k / VST) & 1u, 8, k, false);
+        if (k >= SST) wait_wd(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k, false);
+        const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
+        uint32_t slo[4], shi[4], clo[4], chi[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double2 tn = vv[e];                      // (t, 1/N)
+          const double ph = __dmul_rn(omega, tn.x);      // ((2*pi)*f)*t, rounded once more
+          double s, cs;
+          if (fast) sincos_cw(ph, &s, &cs);
+          else sincos_library(ph, &s, &cs);              // beyond the Cody-Waite range (or NaN/Inf): library path
+          const double sn = s * tn.y, cn = cs * tn.y;
+          s3[0] = fma(sn, s, s3[0]);
+          s3[1] = fma(sn, cs, s3[1]);
+          s3[2] = fma(cn, cs, s3[2]);
+          const uint2 ds = digits7(s), dc = digits7(cs);
+          slo[e] = ds.x; shi[e] = ds.y; clo[e] = dc.x; chi[e] = dc.y;
+        }
+        // 4 x 7 byte transpose: word of plane p (most significant first) = byte (6 - p) of the four values
+        unsigned char* sb = sm.S + ss * S_STAGE + soff;
+        {
+          const uint32_t a = __byte_perm(slo[0], slo[1], 0x5140), b = __byte_perm(slo[0], slo[1], 0x7362);
+          const uint32_t c2 = __byte_perm(slo[2], slo[3], 0x5140), d = __byte_perm(slo[2], slo[3], 0x7362);
+          const uint32_t e2 = __byte_perm(shi[0], shi[1], 0x5140), f2 = __byte_perm(shi[0], shi[1], 0x7362);
+          const uint32_t g2 = __byte_perm(shi[2], shi[3], 0x5140), h2 = __byte_perm(shi[2], shi[3], 0x7362);
+          *reinterpret_cast<uint32_t*>(sb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);   // byte 0
+          *reinterpret_cast<uint32_t*>(sb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);   // byte 1
+          *reinterpret_cast<uint32_t*>(sb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);    // byte 2
+          *reinterpret_cast<uint32_t*>(sb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);    // byte 3
+          *reinterpret_cast<uint32_t*>(sb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);  // byte 4
+          *reinterpret_cast<uint32_t*>(sb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);  // byte 5
+          *reinterpret_cast<uint32_t*>(sb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);  // byte 6
+        }
+        {
+          unsigned char* cb = sb + NF * KT;  // cos rows 32..63
+          const uint32_t a = __byte_perm(clo[0], clo[1], 0x5140), b = __byte_perm(clo[0], clo[1], 0x7362);
+          const uint32_t c2 = __byte_perm(clo[2], clo[3], 0x5140), d = __byte_perm(clo[2], clo[3], 0x7362);
+          const uint32_t e2 = __byte_perm(chi[0], chi[1], 0x5140), f2 = __byte_perm(chi[0], chi[1], 0x7362);
+          const uint32_t g2 = __byte_perm(chi[2], chi[3], 0x5140), h2 = __byte_perm(chi[2], chi[3], 0x7362);
+          *reinterpret_cast<uint32_t*>(cb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);
+          *reinterpret_cast<uint32_t*>(cb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);
+          *reinterpret_cast<uint32_t*>(cb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);
+          *reinterpret_cast<uint32_t*>(cb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);
+          *reinterpret_cast<uint32_t*>(cb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);
+          *reinterpret_cast<uint32_t*>(cb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);
+          *reinterpret_cast<uint32_t*>(cb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sm.s_full[ss]);
+          mbar_arrive(&sm.v_empty[sv]);
+        }
+      }
+      kbase += (uint32_t)nst;
+      // the three sums of frequency f: over the 8 lanes that share it, then published per producer group
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        double t = s3[q];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        s3[q] = t;
+      }
+      const uint32_t buf = it & 1u;
+      if (it >= 2) wait_wd(&sm.sums_empty[buf], ((it >> 1) - 1) & 1u, 10, it, false);
+      if (kg == 0) {
+        double* o = sm.redA + ((buf * 2 + grp) * NF + f) * 3;
+        o[0] = s3[0]; o[1] = s3[1]; o[2] = s3[2];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.sums_full[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "n"(512));
+}
+
+}  // namespace i8
+
+// ---- host side ------------------------------------------------------------------------------------------------
+// A pack can take the tensor path when every pulsar fits the tile: diagonal N, plain Fp, m + 1 <= 128 rows (the basis
+// rows and the w row), n <= 16384 TOAs (int32 accumulators: 7 products of |digit|^2 <= 2^14 per TOA stay below 2^31
+// up to 18 724 TOAs).
+bool i8_eligible(const fastfp_pack* pk) {
+  if (pk->ecorr || pk->nmfp) return false;
+  for (const PulsarMeta& pm : pk->meta)
+    if (pm.m + 1 > 128 || pm.n > 16384) return false;
+  return true;
+}
+
+// lay out and build the digit planes from the fp64 packets (after launch_fp_precompute); sets pk->i8_ok
+int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
+  pk->i8_ok = false;
+  if (!i8_eligible(pk)) return 0;
+  const int P = pk->P;
+  int64_t off = 0;
+  int rows_max = 0, nst_max = 0;
+  for (PulsarMeta& pm : pk->meta) {
+    pm.i8_rows = (pm.m + 1 + 7) / 8 * 8;
+    pm.i8_nst = (pm.n + i8::KT - 1) / i8::KT;
+    pm.i8_off = off;
+    off += (int64_t)pm.i8_nst * (i8::V_STAGE + i8::NPL * pm.i8_rows * i8::KT);
+    rows_max = pm.i8_rows > rows_max ? pm.i8_rows : rows_max;
+    nst_max = pm.i8_nst > nst_max ? pm.i8_nst : nst_max;
+  }
+  FFP_CUDA(cudaMemcpyAsync(pk->d_meta, pk->meta.data(), sizeof(PulsarMeta) * P, cudaMemcpyHostToDevice, st));
+  // the last plane of the last stage is read 128 rows deep by the MMA only from shared memory; the global buffer
+  // needs no slack, but keep the allocation 16-byte granular for the bulk copies
+  FFP_CUDA(cudaMalloc(&pk->d_i8, (size_t)off + 16));
+  FFP_CUDA(cudaMalloc(&pk->d_i8_scale, (size_t)P * 128 * sizeof(double)));
+  int *d_exp = nullptr, *d_bad = nullptr;
+  FFP_CUDA(cudaMalloc(&d_exp, (size_t)P * 128 * sizeof(int)));
+  FFP_CUDA(cudaMalloc(&d_bad, (size_t)P * sizeof(int)));
+  FFP_CUDA(cudaMemsetAsync(d_bad, 0, (size_t)P * sizeof(int), st));
+  i8::i8_rowscale_kernel<<<dim3(128, P), 256, 0, st>>>(pk->d_packets, pk->d_meta, pk->d_i8_scale, d_exp, d_bad);
+  i8::i8_planes_kernel<<<dim3(nst_max, P), 256, 0, st>>>(pk->d_packets, pk->d_meta, d_exp, pk->d_i8);
+  g_launches += 2;
+  cudaError_t e = cudaGetLastError();
+  std::vector<int> bad(P, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(bad.data(), d_bad, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_exp);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return cuda_fail(e, "build_i8_planes");
+  bool ok = true;
+  for (int p = 0; p < P; ++p) ok = ok && bad[p] == 0 && (p >= (int)pk->info.size() || pk->info[p] == 0);
+  pk->i8_rows_max = rows_max;
+  pk->i8_bytes = off;
+  if (!ok) {  // non-finite G or w (singular Sigma, NaN data): the integer planes cannot carry it
+    cudaFree(pk->d_i8); cudaFree(pk->d_i8_scale);
+    pk->d_i8 = nullptr; pk->d_i8_scale = nullptr;
+    return 0;
+  }
+  if (!pk->d_pidx_all) {
+    std::vector<int> idx(P);
+    for (int p = 0; p < P; ++p) idx[p] = p;
+    FFP_CUDA(cudaMalloc(&pk->d_pidx_all, sizeof(int) * P));
+    FFP_CUDA(cudaMemcpy(pk->d_pidx_all, idx.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+  }
+  pk->bytes += off + (int64_t)P * 128 * 8;
+  pk->i8_ok = true;
+  return 0;
+}
+
+int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st) {
+  using namespace i8;
+  Args a{};
+  a.planes = pk->d_i8;
+  a.rowscale = pk->d_i8_scale;
+  a.meta = pk->d_meta;
+  a.pidx = pk->d_pidx_all;
+  a.freqs = d_freqs;
+  a.F = F;
+  a.terms = d_terms;
+  const int64_t ntile = (F + NF - 1) / NF, nwork = ntile * pk->P;
+  if (nwork > 0x7fffffffLL) { set_error("frequency batch too large for one launch"); return -1; }
+  a.ntile = (int)ntile;
+  a.nwork = (int)nwork;
+  a.gslot = NPL * pk->i8_rows_max * KT;
+  const size_t budget = 220 * 1024 - SMEM_FIXED;
+  int gst = (int)(budget / a.gslot);
+  gst = gst > 8 ? 8 : gst;
+  // the last plane of the last slot is read 128 rows deep: the S ring behind the G ring absorbs the overrun
+  if (gst < 2) { set_error("internal: no room for the G ring"); return FASTFP_ERR_UNSUPPORTED; }
+  a.gst = gst;
+  const size_t smem = (size_t)gst * a.gslot + SMEM_FIXED;
+  static bool attr_done[64] = {};
+  if (!attr_done[pk->device & 63]) {
+    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done[pk->device & 63] = true;
+  }
+  const unsigned grid = (unsigned)(nwork < pk->num_sms ? nwork : pk->num_sms);
+  fp_sweep_i8_kernel<<<grid, THREADS, smem, st>>>(a);
+  g_launches += 1;
+  FFP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ffp

@@ -121,9 +121,13 @@ class FastFp(_PackCache):
         (``fastfp/fastfp.py:44-45``)
     :param pta: stored and never used in compute, as in the reference (``fastfp.py:42``)
     :param device: CUDA device ordinal (extension; default 0 or ``LOCAL_RANK``)
+    :param path: which kernel sweeps (extension): ``"auto"`` (default; also from ``FASTFP_B200_PATH``) = the
+        INT8 tensor-core kernel (``tcgen05``, exact digit-plane product) when every pulsar fits its tile,
+        else the fp64 DMMA kernel; ``"fp64"`` / ``"i8"`` force one (``"i8"`` raises if the pack cannot take it).
+        Both meet the same parity bar; see DESIGN.md.
     """
 
-    def __init__(self, psrs, pta=None, device=None):
+    def __init__(self, psrs, pta=None, device=None, path=None):
         self.psrs = psrs
         self.pta = pta
         self.toas = [np.asarray(psr.toas, dtype=np.float64) for psr in psrs]
@@ -133,6 +137,11 @@ class FastFp(_PackCache):
 
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = int(device)
+        import os as _os
+
+        self.path = path if path is not None else _os.environ.get("FASTFP_B200_PATH", "auto")
+        if self.path not in ("auto", "fp64", "i8"):
+            raise ValueError("path must be 'auto', 'fp64' or 'i8'")
 
     # -- packing (one-time, frequency-independent precompute on the device) -----------------
     def _build_pack(self, lists):
@@ -140,8 +149,12 @@ class FastFp(_PackCache):
 
         Nvecs, Ts, sigmas = lists
         if any(blockn.is_block(N) for N in Nvecs):  # block-diagonal N (kernel ECORR)
-            return _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
-        return _cabi.Pack.create_fp(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
+            pack = _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
+        else:
+            pack = _cabi.Pack.create_fp(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
+        if self.path != "auto":
+            pack.set_path(self.path)
+        return pack
 
     def prepare(self, Nvecs, Ts, sigmas, force=False):
         """Upload and pre-reduce the per-pulsar arrays. The pack is cached and keyed on the full contents

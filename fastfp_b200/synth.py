@@ -112,19 +112,33 @@ def make_pta(
     white_only: bool = False,
     inc_cp: bool = True,
     seed: int = SEED0,
+    epoch: int = 0,
+    nbackends: int = 2,
 ) -> SynthPTA:
     """Build a synthetic PTA.
 
     ``n`` and ``n_tm`` may be ints or per-pulsar sequences (ragged arrays are the norm in
     the reference: its pulsar axis is a Python loop, ``fastfp/fastfp.py:72-74``).
     ``white_only=True`` gives config C1: ``T`` holds only the timing-model columns.
+    ``epoch > 1`` clusters the TOAs into observing epochs of ``epoch`` TOAs 0.2 s apart (what ECORR models),
+    epochs alternating between ``nbackends`` receiver backends (``psr.backend_flags``); see :func:`with_ecorr`.
     """
     ns = [int(n)] * P if np.isscalar(n) else [int(v) for v in n]
     ntms = [int(n_tm)] * P if np.isscalar(n_tm) else [int(v) for v in n_tm]
     assert len(ns) == P and len(ntms) == P
 
     rngs = [np.random.default_rng(seed + p) for p in range(P)]
-    toas = [MJD0_SECONDS + np.sort(r.uniform(0.0, SPAN_YEARS * const.yr, size=k)) for r, k in zip(rngs, ns)]
+    if epoch > 1:
+        toas, flags = [], []
+        for r, k in zip(rngs, ns):
+            nep = -(-k // epoch)
+            t0 = MJD0_SECONDS + np.sort(r.uniform(0.0, SPAN_YEARS * const.yr, size=nep))
+            t0 = t0 + 10.0 * np.arange(nep)  # keep epochs at least 10 s apart
+            toas.append((t0[:, None] + 0.2 * np.arange(epoch)[None, :]).reshape(-1)[:k])
+            flags.append(np.repeat(np.array([f"be{e % nbackends}" for e in range(nep)]), epoch)[:k])
+    else:
+        toas = [MJD0_SECONDS + np.sort(r.uniform(0.0, SPAN_YEARS * const.yr, size=k)) for r, k in zip(rngs, ns)]
+        flags = [np.array(["synth"] * k) for k in ns]
     Tspan = float(max(t.max() for t in toas) - min(t.min() for t in toas))
     Ffreqs = None if white_only else np.repeat(np.arange(1, ncomps + 1) / Tspan, 2)
 
@@ -167,7 +181,7 @@ def make_pta(
                 toas=t,
                 residuals=r,
                 Mmat=U,
-                backend_flags=np.array(["synth"] * t.size),
+                backend_flags=flags[p],
             )
         )
         Nvecs.append(Nvec)
@@ -176,6 +190,39 @@ def make_pta(
         phis.append(phi)
         sigmas.append(TNT + np.diag(1.0 / phi))  # reference fastfp/utils.py:76
     return SynthPTA(psrs, Nvecs, Ts, TNTs, phis, sigmas, noise, Tspan, Ffreqs, ntms, ncomps, inc_cp and not white_only)
+
+
+def with_ecorr(pta: SynthPTA, kernel: bool = False, seed: int = SEED0 + 555):
+    """ECORR on top of a PTA made with ``epoch > 1``: per (pulsar, backend) a ``log10_ecorr`` in ``[-7, -6]`` added
+    to ``pta.noise`` under the key :class:`fastfp_b200.GPEcorr_container` looks up (``fastfp/nmfp.py:447-450``).
+    Returns ``(Nvecs, Ts, TNTs, phis)`` for
+
+    * ``kernel=False`` -- the GP form the reference implements: ``T = [tm | U | Fourier]`` with the epoch-indicator
+      columns ``U`` (backend by backend), ``phi = [1e40 | 10^(2 log10_ecorr) | red noise]``, diagonal ``N``;
+    * ``kernel=True`` -- the block-diagonal ``N`` (:class:`fastfp_b200.BlockNvec`) with the unchanged basis."""
+    from . import model
+
+    rng = np.random.default_rng(seed)
+    Nvecs, Ts, TNTs, phis = [], [], [], []
+    for p, q in enumerate(pta.psrs):
+        for val in np.unique(q.backend_flags):
+            pta.noise[f"{q.name}_basis_ecorr_{val}_log10_ecorr"] = float(rng.uniform(-7.0, -6.0))
+        ntm = pta.n_tm[p]
+        if kernel:
+            B = model.kernel_ecorr_blocks(q, pta.Nvecs[p], pta.noise)
+            TNT = pta.Ts[p].T @ B.solve(pta.Ts[p])
+            Nvecs.append(B); Ts.append(pta.Ts[p]); phis.append(pta.phis[p])
+        else:
+            U = model.ecorr_basis_by_backend(q)
+            w = model.ecorr_weights_by_backend(q)
+            jv = np.concatenate([wi * 10.0 ** (2.0 * pta.noise[f"{q.name}_basis_ecorr_{val}_log10_ecorr"])
+                                 for wi, val in zip(w, np.unique(q.backend_flags))]) if U.shape[1] else np.zeros(0)
+            T = np.ascontiguousarray(np.concatenate((pta.Ts[p][:, :ntm], U, pta.Ts[p][:, ntm:]), axis=1))
+            TNT = T.T @ (T / pta.Nvecs[p][:, None])
+            Nvecs.append(pta.Nvecs[p]); Ts.append(T)
+            phis.append(np.concatenate((pta.phis[p][:ntm], jv, pta.phis[p][ntm:])))
+        TNTs.append(0.5 * (TNT + TNT.T))
+    return Nvecs, Ts, TNTs, phis
 
 
 def fp_freqs(F: int) -> np.ndarray:

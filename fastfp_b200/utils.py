@@ -6,9 +6,8 @@
   ``get_ndiag``, ``get_basis``); the return orders differ exactly as in the reference.
 * :func:`compute_TNTs` / :func:`compute_sigmas` -- device-side ``T^T N^-1 T (+ diag(phiinv))`` from the
   raw basis (no reference counterpart, ``enterprise`` does this on the host).
-* :func:`initialize_pta` -- ``fastfp/utils.py:104-163`` needs the third-party ``enterprise``
-  packages and is out of this engine's scope; it raises a clear
-  error when they are absent.
+* :func:`initialize_pta` -- ``fastfp/utils.py:104-163``: a pass-through to the third-party ``enterprise``
+  packages where they are installed; it raises a clear error when they are absent.
 """
 from __future__ import annotations
 
@@ -79,11 +78,31 @@ def compute_sigmas(Nvecs, Ts, phiinvs, device: int = 0):
     return out
 
 
-def initialize_pta(*args, **kwargs):
-    """Model construction with ``enterprise`` (reference ``utils.py:104-163``): out of scope for
-    this engine; build the PTA with the reference's own helper and pass it to
-    :func:`get_mats_fp` / :func:`get_mats_nmfp`."""
-    raise NotImplementedError(
-        "initialize_pta builds an enterprise PTA (third-party model construction) and is not part "
-        "of the B200 hot path; construct the PTA with enterprise/fastfp and hand it to get_mats_*"
-    )
+def initialize_pta(psrs, noise, inc_cp=True, rn_comps=30, gwb_comps=30, simple_wn=True, inc_ecorr=False,
+                   select="backend"):
+    """Model construction with ``enterprise`` (reference ``utils.py:104-163``; same arguments, defaults and signal
+    order ``timing model + white noise + red noise (+ common red noise)``, so ``pta.get_basis`` column order
+    matches the phi layouts of :class:`fastfp_b200.RN_container`). A thin pass-through to the third-party
+    packages: it is only available where ``enterprise`` and ``enterprise_extensions`` are installed, and raises
+    ``NotImplementedError`` with guidance otherwise. Nothing of the hot path depends on
+    it: any object with ``get_phiinv`` / ``get_TNT`` / ``get_ndiag`` / ``get_basis`` works with ``get_mats_*``."""
+    try:
+        from enterprise.signals import gp_signals, parameter, signal_base, white_signals
+        from enterprise_extensions import blocks, model_utils
+    except ImportError as exc:
+        raise NotImplementedError(
+            "initialize_pta builds an enterprise PTA (third-party model construction) and needs the `enterprise` "
+            "and `enterprise_extensions` packages, which are not installed here; construct the PTA with "
+            "enterprise/fastfp and hand it to get_mats_fp / get_mats_nmfp, or pass the matrices directly"
+        ) from exc
+    span = model_utils.get_tspan(psrs)
+    if simple_wn:      # EFAC fixed to 1: simulated data sets
+        white = white_signals.MeasurementNoise(efac=parameter.Constant(1.0))
+    else:              # per-backend EFAC/EQUAD, optionally ECORR as a Gaussian process on an epoch basis
+        white = blocks.white_noise_block(inc_ecorr=bool(inc_ecorr), gp_ecorr=bool(inc_ecorr), select=select)
+    signal = gp_signals.TimingModel(use_svd=True) + white + blocks.red_noise_block(Tspan=span, components=rn_comps)
+    if inc_cp:
+        signal = signal + blocks.common_red_noise_block(Tspan=span, components=gwb_comps)
+    pta = signal_base.PTA([signal(psr) for psr in psrs])
+    pta.set_default_params(noise)
+    return pta

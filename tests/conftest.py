@@ -15,6 +15,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(params=["auto", "fp64"])
+def sweep_path(request, monkeypatch):
+    """Run a plain-Fp GPU test on both sweep kernels: "auto" = the INT8 tensor-core kernel wherever the pack can take
+    it (else the fp64 DMMA kernel), "fp64" = the DMMA kernel always. FastFp reads FASTFP_B200_PATH at construction."""
+    monkeypatch.setenv("FASTFP_B200_PATH", request.param)
+    return request.param
+
+
 class Psr:
     """Duck-typed pulsar: all the hot path reads (reference fastfp/fastfp.py:44-45)."""
 

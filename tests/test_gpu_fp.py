@@ -9,7 +9,7 @@ from fastfp_b200 import _cabi, synth
 from oracle import fp_oracle as o
 from oracle import truth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("sweep_path")]
 
 
 def _args(g):

@@ -26,6 +26,7 @@ def c4():
     return synth.make_config("C4")
 
 
+@pytest.mark.usefixtures("sweep_path")
 def test_c4_shape_terms_against_truth(c4):
     pta = c4
     assert pta.P == 68 and pta.Ts[0].shape == (10_000, 72)
@@ -55,6 +56,7 @@ def test_c4_shape_terms_against_truth(c4):
     np.testing.assert_array_equal(fp(freqs, *a), acc)
 
 
+@pytest.mark.usefixtures("sweep_path")
 def test_c4_shape_bins_do_not_depend_on_their_batch(c4):
     """A bin's value must not depend on which tile / launch / rank it was computed in (this is what makes the
     NCCL-gathered sweep equal to the single-GPU sweep): slices of the 1e6 grid recomputed alone, shifted by

@@ -21,6 +21,7 @@ def _shape(rng):
     return P, n_tm, ncomps, ns
 
 
+@pytest.mark.usefixtures("sweep_path")
 @pytest.mark.parametrize("seed", range(12))
 def test_random_small_fp(seed):
     rng = np.random.default_rng(1000 + seed)
