@@ -497,6 +497,7 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
     torch.cuda.synchronize()
     kern_ms = ks.elapsed_time(ke) / nk
     pack_bytes = pack.nbytes
+    sweep_path = pack.path
     fp.invalidate()  # free this workload's device pack before the next one is built
 
     if rank != 0:
@@ -508,6 +509,47 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
     traffic, traffic_src = measured_traffic(key)
     fp64_peak, _ = _cabi.fp64_peak(1, 20000, device=ctx.local)  # DMMA loop, same pipe as DFMA
     ach_tf = evals_kernel * flops_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e12
+    if sweep_path == "i8":
+        # The contraction runs on the INT8 tensor path: Y = G [s c] as 28 products of 8-bit digit planes
+        # (tcgen05.mma kind::i8, exact int32 accumulation). Algorithmic integer ops per eval: 28 plane products
+        # x 2 (multiply, add) x 2 columns (sin, cos) x (m + 1) rows (basis + the C^-1 r row) x n TOAs.
+        i8_peak, _ = _cabi.fp64_peak(17, 2000, device=ctx.local)
+        i8_shape, _ = _cabi.fp64_peak(18, 4000, device=ctx.local)
+        ops_eval = 28.0 * 2.0 * 2.0 * (M_BASIS + 1) * wl["n"]
+        ach_top = evals_kernel * ops_eval / (kern_ms * 1e-3) / 1e12
+        nst = -(-wl["n"] // 32)
+        items = wl["P"] * -(-(hi - lo) // 32)
+        exec_top = items * nst * 28.0 * 2.0 * 128 * 64 * 32 / (kern_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "pipe": "INT8 tensor path (tcgen05.mma kind::i8, int32 accumulators in tensor memory)",
+            "achieved": ach_top, "peak": i8_peak, "unit": "TOP/s", "frac": ach_top / i8_peak,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": "measured live on this GPU: fastfp_fp64_peak kind 17 (back-to-back kind::i8 MMAs, M=128 N=256 K=32, "
+                           "one issuing thread per SM); MEASURED_PEAKS.json holds a bf16 figure only",
+            "kernel": "fp_sweep_i8_kernel (persistent, warp-specialised: TMA / MMA issue / epilogue / sincos producers)",
+            "kernel_ms": kern_ms, "ops_per_eval": ops_eval,
+            "shape_bound": {"achieved": exec_top, "peak": i8_shape, "unit": "TOP/s", "frac": exec_top / i8_shape,
+                            "note": "executed MMA work (128-row operand, of which m + 1 = 73 rows are real) against the "
+                                    "same 28-product stage issued back to back (kind 18): an M=128 N=64 K=32 MMA reads 6 KB "
+                                    "of operands from shared memory = 48 cycles at 128 B/clk, against 32 cycles of tensor "
+                                    "time -- shared-memory operand bandwidth is what binds this formulation (TMEM holds "
+                                    "7 accumulators x 64 columns, so N cannot grow)"},
+            "fp64_equivalent": {"achieved": ach_tf, "unit": "TFLOP/s", "fp64_pipe_peak": fp64_peak,
+                                "ratio": ach_tf / fp64_peak,
+                                "note": "the same statistic in fp64 flops (4m+10)n per eval against the fp64 pipe peak the "
+                                        "DMMA kernel is bound by (round 1: 0.68): above 1 because the contraction left that pipe"},
+            "note": "algorithmic INT8 ops = 112 (m+1) n per eval; padding rows of the 128-row operand and the producers' "
+                    "fp64 sincos work are not counted"}
+    else:
+        roofline = {"bound": "tensor", "pipe": "fp64 tensor path (DMMA; DFMA shares the pipe)",
+                    "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
+                                   "MEASURED_PEAKS.json holds no fp64 figure",
+                    "kernel": "fp_sweep_kernel (persistent, warp-specialised)", "kernel_ms": kern_ms,
+                    "flops_per_eval": flops_per_eval(wl["n"], M_BASIS),
+                    "note": "algorithmic flops (4m+10)n per eval: Y = G[s c] and the five weighted sums; the "
+                            "sincos generation that must also run on this pipe is not counted"}
     line = {
         "metric": METRIC, "value": evals_step / ms_step * 1e3, "unit": "evals/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
@@ -518,6 +560,7 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
                 "l2": "256 MiB buffer written between timed steps (L2 flush); packed inputs are "
                       f"{pack_bytes / 2**20:.0f} MiB per GPU",
                 "pack_ms_one_time": pack_ms, "content_hash_ms_per_call": hash_ms,
+                "sweep_kernel": {"i8": "INT8 tensor-core kernel (tcgen05 / TMEM)", "fp64": "fp64 DMMA kernel"}[sweep_path],
                 "freqs_total": F_total, "evals_per_step": evals_step},
         "e2e": {"value": evals_step / e2e_ms * 1e3, "unit": "evals/s", "ms_per_step": e2e_ms, "steps": ne2e,
                 "h2d_bytes_per_step": int(8 * F_total), "d2h_bytes_per_step": int(8 * F_total * world),
@@ -526,17 +569,7 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "checks": checks,
-        # The binding roofline: the contraction runs on the fp64 tensor path (DMMA), which shares one
-        # pipe with DFMA; peak = the same pipe measured on this GPU with a pure mma.m8n8k4.f64 loop.
-        "roofline": {"bound": "tensor", "pipe": "fp64 tensor path (DMMA; DFMA shares the pipe)",
-                     "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                     "traffic": traffic, "traffic_source": traffic_src,
-                     "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
-                                    "MEASURED_PEAKS.json holds no fp64 figure",
-                     "kernel": "fp_sweep_kernel (persistent, warp-specialised)", "kernel_ms": kern_ms,
-                     "flops_per_eval": flops_per_eval(wl["n"], M_BASIS),
-                     "note": "algorithmic flops (4m+10)n per eval: Y = G[s c] and the five weighted sums; the "
-                             "sincos generation that must also run on this pipe is not counted"},
+        "roofline": roofline,
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "algorithmic bytes 8(n(m+3)+m^2) per eval (the reference's streaming model); "
@@ -733,6 +766,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--sweep-path", choices=["auto", "fp64", "i8"], default=None,
+                    help="kernel of the plain-Fp sweep (default auto: the INT8 tensor-core kernel when the pack fits it)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")
@@ -750,6 +785,8 @@ def main():
     if os.environ.get("FASTFP_B200_NVCC_FLAGS") and not os.environ.get("FASTFP_BENCH_ALLOW_DBG"):
         raise SystemExit("FASTFP_B200_NVCC_FLAGS is set: bench.py only measures the library as shipped")
 
+    if args.sweep_path:
+        os.environ["FASTFP_B200_PATH"] = args.sweep_path
     ctx = Ctx(rank, world, local)
     runner = run_nmfp if wl["kind"] == "nmfp" else run_fp
     line = runner(key, wl, ctx, args.steps, args.warmup, not args.no_cpu_baseline)

@@ -34,6 +34,8 @@ SYMBOLS = {
     ),
     "fastfp_fp_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "fastfp_fp_terms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "fastfp_fe_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_int, C.c_void_p]),
     "fastfp_nmfp_pack_create": (
         C.c_int,
         [C.c_int, C.c_int, c_int64_p, c_int64_p, c_double_pp, c_double_pp, c_double_pp, c_double_pp,
@@ -318,6 +320,33 @@ class Pack:
             flags |= OUT_ON_DEVICE
         fn = lib.fastfp_fp_terms if terms else lib.fastfp_fp_sweep
         check(fn(self._h, _vp(fptr), F, _vp(optr), flags, C.c_void_p(stream)))
+        return ret
+
+    def fe_sweep(self, freqs, fplus, fcross, out=None, stream: int = 0):
+        """Fe-statistic for ``S`` sky positions: ``fplus``, ``fcross`` host arrays ``(S, P)``; returns / fills
+        ``(S, F)``. ``freqs`` / ``out`` as in :meth:`fp_sweep`."""
+        lib = load()
+        fplus, fcross = as_f64(fplus), as_f64(fcross)
+        if fplus.ndim != 2 or fplus.shape != fcross.shape or fplus.shape[1] != self.P:
+            raise ValueError("fplus and fcross must both have shape (n_sky, n_pulsars)")
+        S = fplus.shape[0]
+        flags = 0
+        if isinstance(freqs, tuple):
+            fptr, F = freqs
+            flags |= FREQS_ON_DEVICE
+        else:
+            freqs = as_f64(freqs).reshape(-1)
+            fptr, F = freqs, freqs.shape[0]
+        ret = None
+        if out is None:
+            ret = np.empty((S, F), dtype=np.float64)
+            optr = ret
+        elif isinstance(out, np.ndarray):
+            optr = out
+        else:
+            optr = out
+            flags |= OUT_ON_DEVICE
+        check(lib.fastfp_fe_sweep(self._h, _vp(fptr), F, _vp(fplus), _vp(fcross), S, _vp(optr), flags, C.c_void_p(stream)))
         return ret
 
     def nmfp_sweep(self, freqs, phiinv_var, D: int, out=None, stream: int = 0):

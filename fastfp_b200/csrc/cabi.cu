@@ -168,7 +168,7 @@ static void pack_free(fastfp_pack* pk) {
   cudaFree(pk->d_S0); cudaFree(pk->d_zr); cudaFree(pk->d_slab); cudaFree(pk->d_counter); cudaFree(pk->d_done_mask);
   cudaFree(pk->d_terms); cudaFree(pk->d_freqs); cudaFree(pk->d_out); cudaFree(pk->d_scratch);
   cudaFree(pk->d_pl); cudaFreeHost(pk->h_pl);
-  cudaFree(pk->d_i8); cudaFree(pk->d_i8_scale); cudaFree(pk->d_pidx_all);
+  cudaFree(pk->d_i8); cudaFree(pk->d_i8_scale); cudaFree(pk->d_pidx_all); cudaFree(pk->d_inner);
   if (pk->pl_event) cudaEventDestroy(pk->pl_event);
   delete pk;
 }
@@ -370,9 +370,11 @@ int fastfp_pack_factor_info(const fastfp_pack_t* pack, int32_t* info) {
 static const int64_t kTermBudgetDoubles = 1LL << 27;  // 1 GiB
 
 // per-pulsar terms of one frequency batch on the path the pack is set to
-static int sweep_terms(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st) {
+static int sweep_terms(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
+                       double* d_inner = nullptr) {
   const bool i8 = pk->i8_ok && pk->path != FASTFP_PATH_FP64;
-  return i8 ? launch_fp_sweep_i8(pk, d_freqs, F, d_terms, st) : launch_fp_sweep(pk, d_freqs, F, d_terms, st);
+  return i8 ? launch_fp_sweep_i8(pk, d_freqs, F, d_terms, st, d_inner)
+            : launch_fp_sweep(pk, d_freqs, F, d_terms, st, nullptr, d_inner);
 }
 
 static int fp_run(const fastfp_pack* pk, const double* freqs, int64_t F, double* out, int flags,
@@ -432,6 +434,51 @@ int fastfp_fp_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F, d
 int fastfp_fp_terms(const fastfp_pack_t* pack, const double* freqs, int64_t F, double* terms,
                     int flags, void* stream) {
   return fp_run(pack, freqs, F, terms, flags, stream, true);
+}
+
+// Fe-statistic sky scan: one sweep for the inner products of every (pulsar, frequency), then the combine kernel
+int fastfp_fe_sweep(const fastfp_pack_t* pk, const double* freqs, int64_t F, const double* fplus, const double* fcross,
+                    int64_t S, double* out, int flags, void* stream) {
+  if (!pk || F < 0 || S < 0 || ((F > 0 && S > 0) && (!freqs || !fplus || !fcross || !out))) {
+    set_error("fastfp_fe_sweep: null argument or negative size");
+    return FASTFP_ERR_INVALID;
+  }
+  if (pk->nmfp) { set_error("fastfp_fe_sweep needs a plain-Fp pack (fastfp_pack_create)"); return FASTFP_ERR_INVALID; }
+  if (F == 0 || S == 0) return FASTFP_OK;
+  DeviceGuard g(pk->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fdev = flags & FASTFP_FREQS_ON_DEVICE, odev = flags & FASTFP_OUT_ON_DEVICE;
+  const int P = pk->P;
+  const double* d_freqs = freqs;
+  if (!fdev) {
+    if (int rc = ensure(&pk->d_freqs, &pk->freqs_cap, F)) return rc;
+    FFP_CUDA(cudaMemcpyAsync(pk->d_freqs, freqs, (size_t)F * 8, cudaMemcpyHostToDevice, st));
+    d_freqs = pk->d_freqs;
+  }
+  double* d_out = out;
+  if (!odev) {
+    if (int rc = ensure(&pk->d_out, &pk->out_cap, S * F)) return rc;
+    d_out = pk->d_out;
+  }
+  const int64_t FB = std::max<int64_t>(1024, std::min<int64_t>(F, kTermBudgetDoubles / (5 * (int64_t)P)));
+  // scratch: the inner products of one frequency batch, then the antenna patterns of the S sky positions
+  if (int rc = ensure(&pk->d_inner, &pk->inner_cap, 5 * (int64_t)P * std::min(FB, F) + 2 * S * P)) return rc;
+  double* d_fp = pk->d_inner + 5 * (int64_t)P * std::min(FB, F);
+  double* d_fx = d_fp + S * P;
+  FFP_CUDA(cudaMemcpyAsync(d_fp, fplus, (size_t)S * P * 8, cudaMemcpyHostToDevice, st));
+  FFP_CUDA(cudaMemcpyAsync(d_fx, fcross, (size_t)S * P * 8, cudaMemcpyHostToDevice, st));
+  for (int64_t lo = 0; lo < F; lo += FB) {
+    const int64_t fb = std::min(FB, F - lo);
+    if (int rc = sweep_terms(pk, d_freqs + lo, fb, nullptr, st, pk->d_inner)) return rc;
+    if (int rc = launch_fe_combine(pk->d_inner, P, fb, d_fp, d_fx, S, d_out + lo, F, st)) return rc;
+  }
+  if (!odev) {
+    FFP_CUDA(cudaMemcpyAsync(out, d_out, (size_t)S * F * 8, cudaMemcpyDeviceToHost, st));
+    FFP_CUDA(cudaStreamSynchronize(st));
+  } else {
+    FFP_CUDA(cudaStreamSynchronize(st));  // fplus / fcross were read from caller-owned host memory
+  }
+  return FASTFP_OK;
 }
 
 int fastfp_nmfp_sweep(const fastfp_pack_t* pk, const double* freqs, int64_t F,
@@ -577,12 +624,13 @@ int fastfp_tnt(int device, int64_t n, int64_t m, const double* Nvec, const doubl
 }
 
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms) {
-  if (!tflops || !ms || iters < 1 || kind < 0 || kind > 16) {
+  if (!tflops || !ms || iters < 1 || kind < 0 || kind > 18) {
     set_error("fastfp_fp64_peak: invalid argument");
     return FASTFP_ERR_INVALID;
   }
   DeviceGuard g(device);
   if (!g.ok) { set_error("cannot select CUDA device"); return FASTFP_ERR_CUDA; }
+  if (kind >= 17) return run_i8_peak(kind, iters, tflops, ms);
   return run_fp64_peak(kind, iters, tflops, ms);
 }
 

@@ -157,6 +157,8 @@ struct fastfp_pack {
   mutable int64_t out_cap = 0;
   mutable double* d_scratch = nullptr;
   mutable int64_t scratch_cap = 0;
+  mutable double* d_inner = nullptr;   // Fe-statistic: inner products of a frequency batch + antenna patterns
+  mutable int64_t inner_cap = 0;
   // staging of the per-draw power-law parameters (fastfp_powerlaw_phiinv): device + pinned host copy,
   // the event marks the last H2D copy out of h_pl; pl_tab is the frequency table already on the device
   mutable double* d_pl = nullptr;
@@ -199,12 +201,17 @@ struct NmfpOut {      // stage-A outputs of the nmfp path (null for plain Fp)
   int mvmax;          // padded width of the per-draw block (multiple of 8)
 };
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
-                    cudaStream_t st, const NmfpOut* nm = nullptr);
+                    cudaStream_t st, const NmfpOut* nm = nullptr, double* d_inner = nullptr);
 int launch_reduce_terms(const double* d_terms, int P, int64_t F, double* d_out, cudaStream_t st);
 // fp_sweep_i8.cu
 bool i8_eligible(const fastfp_pack* pk);
 int build_i8_planes(fastfp_pack* pk, cudaStream_t st);
-int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st);
+int run_i8_peak(int kind, int iters, double* tops, double* ms);
+int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
+                       double* d_inner = nullptr);
+// fe.cu
+int launch_fe_combine(const double* d_inner, int P, int64_t F, const double* d_fplus, const double* d_fcross, int64_t S,
+                      double* d_out, int64_t out_ld, cudaStream_t st);
 bool sweep_config(int m, KernelCfg* cfg);
 int sweep_max_slab_doubles();
 // xcy.cu

@@ -32,7 +32,7 @@ __global__ void reduce_terms_kernel(const double* __restrict__ terms, int P, int
 }
 
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
-                    cudaStream_t st, const NmfpOut* nm) {
+                    cudaStream_t st, const NmfpOut* nm, double* d_inner) {
 #ifdef FFP_DEBUG_SWITCHES  // profiling builds only; the shipped library is compiled without it
   static const int dbg = getenv("FASTFP_DBG") ? atoi(getenv("FASTFP_DBG")) : 0;
 #endif
@@ -42,6 +42,7 @@ int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, dou
   a.freqs = d_freqs;
   a.F = F;
   a.terms = d_terms;
+  a.inner = d_inner;
   a.slab = pk->d_slab;
   a.counter = pk->d_counter;
   a.Z = nm ? nm->Z : nullptr;

@@ -48,7 +48,7 @@ constexpr int V_STAGE = KT * 16;       // (t, 1/N) per TOA
 constexpr int SST = 6, VST = 8;        // ring depths (even: a slot is always served by the same producer group)
 constexpr int THREADS = 768;
 constexpr int NPW = 16;                // producer warps
-constexpr int REGS_LAUNCH = 80, REGS_CTRL = 40, REGS_EPI = 144, REGS_PROD = 72;
+constexpr int REGS_LAUNCH = 80, REGS_CTRL = 56, REGS_EPI = 136, REGS_PROD = 72;
 static_assert(128 * REGS_CTRL + 128 * REGS_EPI + 512 * REGS_PROD <= THREADS * REGS_LAUNCH, "register pool");
 static_assert(SST % 2 == 0 && VST % 2 == 0, "ring depths must be even");
 
@@ -60,6 +60,7 @@ struct Args {
   const double* freqs;
   int64_t F;
   double* terms;                 // [P][F]
+  double* inner;                 // optional [P][F][5]: (s|s), (s|c), (c|c), (s|r), (c|r); null = terms only
   int ntile, nwork;
   int gslot, gst;                // G ring: bytes per slot (7 x rows_max x 32), number of slots
 };
@@ -202,7 +203,7 @@ __device__ __forceinline__ uint2 digits7(double x) {
 // Every wait of this kernel is bounded: a protocol error would otherwise hang the GPU. No legitimate wait is longer
 // than a few stages (microseconds); after ~2 s of polling the CTA reports where it was stuck and traps, which the
 // host sees as a launch failure instead of a hung device.
-__device__ __noinline__ void wait_timeout(int tag, uint32_t k) {
+__device__ __forceinline__ void wait_timeout(int tag, uint32_t k) {
   printf("[fastfp_b200 i8 sweep] mbarrier wait timed out: tag %d, stage/item %u, block %d, warp %d\n", tag, k,
          (int)blockIdx.x, (int)(threadIdx.x >> 5));
   __trap();
@@ -443,7 +444,11 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
         double val = 0.5 * (N0 * x0 + N1 * x1);
         if (fidx < ar.F) {
           if (!(ar.freqs[fidx] > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);  // f <= 0: NaN like f**(1/3)
-          ar.terms[(size_t)p * ar.F + fidx] = val;
+          if (ar.terms) ar.terms[(size_t)p * ar.F + fidx] = val;
+          if (ar.inner) {
+            double* o = ar.inner + ((size_t)p * ar.F + fidx) * 5;
+            o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; o[3] = N0; o[4] = N1;
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.sums_empty[buf]);
@@ -550,7 +555,81 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
   if (wid == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "n"(512));
 }
 
+// ---- measurement helper: the tensor path's own ceilings (fastfp_fp64_peak kinds 17 and 18) -----------------------
+// Back-to-back kind::i8 MMAs from one thread per CTA, one CTA per SM, operands in the sweep kernel's SWIZZLE_32B planes:
+// N = 256 gives the INT8 tensor peak of the chip, N = 64 with the sweep's 28-product stage gives the rate this
+// formulation can reach at most (an M=128, N=64 MMA is bound by its 6 KB of shared-memory operand reads).
+template <int N>
+__global__ void __launch_bounds__(64, 1) i8_peak_kernel(int iters, int* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_base;
+  __shared__ __align__(8) uint64_t bar;
+  constexpr int A_PLANE = 128 * KT, B_PLANE = N * KT;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + NPL * A_PLANE;
+  for (int i = threadIdx.x; i < NPL * (A_PLANE + B_PLANE); i += blockDim.x) smem[i] = (unsigned char)((i * 7 + 3) & 3);
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < NPL; ++i)
+#pragma unroll
+        for (int j = 0; j < NPL - i; ++j)
+          umma_i8(tm + (uint32_t)(((i + j) * N) % 512), umma_desc(smem_u32(sA + i * A_PLANE)),
+                  umma_desc(smem_u32(sB + j * B_PLANE)), idesc, (it > 0 || i > 0) ? 1u : 0u);
+    }
+    umma_commit(&bar);
+    wait_wd(&bar, 0u, 11, 0u, true);
+    if (out) out[blockIdx.x] = 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "n"(512));
+}
+
 }  // namespace i8
+
+int run_i8_peak(int kind, int iters, double* tops, double* ms_out) {
+  using namespace i8;
+  int dev = 0, sms = 0;
+  FFP_CUDA(cudaGetDevice(&dev));
+  FFP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int N = kind == 17 ? 256 : 64;
+  const size_t smem = (size_t)NPL * (128 + N) * KT + 1024;
+  if (kind == 17) FFP_CUDA(cudaFuncSetAttribute(i8_peak_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else FFP_CUDA(cudaFuncSetAttribute(i8_peak_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  FFP_CUDA(cudaEventCreate(&e0));
+  FFP_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    FFP_CUDA(cudaEventRecord(e0));
+    if (kind == 17) i8_peak_kernel<256><<<sms, 64, smem>>>(iters, nullptr);
+    else i8_peak_kernel<64><<<sms, 64, smem>>>(iters, nullptr);
+    FFP_CUDA(cudaEventRecord(e1));
+    FFP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    FFP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  g_launches += 4;
+  FFP_CUDA(cudaGetLastError());
+  *tops = 2.0 * (double)sms * iters * 28.0 * 128.0 * N * 32.0 / (best * 1e-3) / 1e12;
+  *ms_out = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
 
 // ---- host side ------------------------------------------------------------------------------------------------
 // A pack can take the tensor path when every pulsar fits the tile: diagonal N, plain Fp, m + 1 <= 128 rows (the basis
@@ -617,7 +696,8 @@ int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
   return 0;
 }
 
-int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st) {
+int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
+                       double* d_inner) {
   using namespace i8;
   Args a{};
   a.planes = pk->d_i8;
@@ -627,6 +707,7 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   a.freqs = d_freqs;
   a.F = F;
   a.terms = d_terms;
+  a.inner = d_inner;
   const int64_t ntile = (F + NF - 1) / NF, nwork = ntile * pk->P;
   if (nwork > 0x7fffffffLL) { set_error("frequency batch too large for one launch"); return -1; }
   a.ntile = (int)ntile;

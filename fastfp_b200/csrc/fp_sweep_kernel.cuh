@@ -47,6 +47,7 @@ struct SweepArgs {
   const double* freqs;
   int64_t F;
   double* terms;          // [P][F] (plain Fp)
+  double* inner;          // optional [P][F][5]: (s|s), (s|c), (c|c), (s|r), (c|r) (Fe-statistic); null = terms only
   double* slab;           // level-2 scratch, SLAB doubles per CTA
   unsigned int* counter;  // work counter (zeroed before the launch)
   double* Z;              // nmfp: [P][ceil(F/32)][mvmax/4][8][32] (B-fragment order, mvmax = padded)
@@ -510,7 +511,11 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
         const double x0 = (n0 - m01 * x1) / m00;
         double val = 0.5 * (a[3] * x0 + a[4] * x1);
         if (!(sm.fq[tid] > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);
-        ar.terms[(size_t)p * ar.F + fidx] = val;
+        if (ar.terms) ar.terms[(size_t)p * ar.F + fidx] = val;
+        if (ar.inner) {  // the inner products themselves (no f^(-1/3) prefactor: it cancels in every statistic)
+          double* o = ar.inner + ((size_t)p * ar.F + fidx) * 5;
+          o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; o[3] = a[3]; o[4] = a[4];
+        }
       }
     }
     __syncthreads();  // B4: fq, red and s_work are reused by the next work item

@@ -104,6 +104,14 @@ def _timing_basis(t: np.ndarray, n_tm: int) -> np.ndarray:
     return np.ascontiguousarray(U)
 
 
+def _sky_position(rng) -> np.ndarray:
+    """isotropic unit vector (``enterprise.pulsar.Pulsar.pos``)"""
+    z = rng.uniform(-1.0, 1.0)
+    ph = rng.uniform(0.0, 2.0 * np.pi)
+    r = np.sqrt(1.0 - z * z)
+    return np.array([r * np.cos(ph), r * np.sin(ph), z])
+
+
 def make_pta(
     P: int,
     n,
@@ -182,6 +190,7 @@ def make_pta(
                 residuals=r,
                 Mmat=U,
                 backend_flags=flags[p],
+                pos=_sky_position(rng),
             )
         )
         Nvecs.append(Nvec)

@@ -91,6 +91,15 @@ int fastfp_pack_path(const fastfp_pack_t* pack);
 int fastfp_fp_terms(const fastfp_pack_t* pack, const double* freqs, int64_t F, double* terms,
                     int flags, void* stream);
 
+/* ---- Fe-statistic (the reference's to-do, README.md:23) ------------------------------------------------
+ * Coherent Earth-term statistic of Ellis, Siemens & Creighton 2012 for S sky positions at once, from the same
+ * per-(pulsar, frequency) inner products as Fp (fastfp/fastfp.py:81-88): with antenna patterns F+_p, Fx_p
+ *   N = sum_p [F+ N_p ; Fx N_p],  M = sum_p [[F+^2 M_p, F+Fx M_p],[F+Fx M_p, Fx^2 M_p]],  Fe = 1/2 N^T M^-1 N
+ * (N_p, M_p as in fastfp.py:83-88; 4x4 general solve with partial pivoting). fplus, fcross: host arrays (S, P)
+ * row-major; out: (S, F) row-major. flags as for fastfp_fp_sweep. One sweep + one combine kernel per call. */
+int fastfp_fe_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F, const double* fplus,
+                    const double* fcross, int64_t S, double* out, int flags, void* stream);
+
 /* ---- noise-marginalised Fp -----------------------------------------------------------
  * fastfp_nmfp_pack_create: NMFP.__init__ (fastfp/nmfp.py:45-51) plus the (TNTs, Nvecs, Ts)
  * of get_mats_nmfp (fastfp/utils.py:97-101). Sigma_d = TNT + diag(phiinv_d) is formed per
@@ -189,7 +198,8 @@ int fastfp_xcy_blockn(int device, int64_t n, int64_t m, const double* Nvec, cons
  * kind 1 as the measured fp64-pipe denominator (MEASURED_PEAKS.json has no fp64 figure). Kinds 3-12
  * are the kernel-design probes of csrc/microbench.cu; 13-15 run the sweep kernel's warp
  * specialisation (8 DMMA warps + 16 DFMA warps) on registers only; 16 = legacy INT8 mma.sync rate
- * (reported as 2 x MAC/s in the same unit). */
+ * (reported as 2 x MAC/s in the same unit); 17 = tcgen05.mma kind::i8 M=128 N=256 (the INT8 tensor peak, TOP/s);
+ * 18 = the tensor sweep's own stage (28 plane products M=128 N=64 K=32: bound by shared-memory operand reads). */
 int fastfp_fp64_peak(int device, int kind, int iters, double* tflops, double* ms);
 
 #ifdef __cplusplus
