@@ -222,8 +222,8 @@ int fastfp_pack_set_path(fastfp_pack_t* pk, int path) {
     return FASTFP_ERR_INVALID;
   }
   if (path == FASTFP_PATH_I8 && !pk->i8_ok) {
-    set_error("fastfp_pack_set_path: this pack has no INT8 digit planes (block-diagonal N, nmfp, m > 127, "
-              "n > 16384 or non-finite data)");
+    set_error("fastfp_pack_set_path: this pack has no INT8 digit planes (block-diagonal N, m > 127, n > 16384 or "
+              "non-finite data)");
     return FASTFP_ERR_UNSUPPORTED;
   }
   pk->path = path;

@@ -208,7 +208,7 @@ bool i8_eligible(const fastfp_pack* pk);
 int build_i8_planes(fastfp_pack* pk, cudaStream_t st);
 int run_i8_peak(int kind, int iters, double* tops, double* ms);
 int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
-                       double* d_inner = nullptr);
+                       double* d_inner = nullptr, const NmfpOut* nm = nullptr);
 // fe.cu
 int launch_fe_combine(const double* d_inner, int P, int64_t F, const double* d_fplus, const double* d_fcross, int64_t S,
                       double* d_out, int64_t out_ld, cudaStream_t st);

@@ -61,6 +61,9 @@ struct Args {
   int64_t F;
   double* terms;                 // [P][F]
   double* inner;                 // optional [P][F][5]: (s|s), (s|c), (c|c), (s|r), (c|r); null = terms only
+  double* Z;                     // nmfp stage A: [P][ceil(F/32)][mvpad/4][8][32] z'_s, z'_c tiles (B-fragment order)
+  double* A;                     // nmfp stage A: [P][ceil(F/32)][5][32] a_ss, a_sc, a_cc, a_sr, a_cr
+  int mvpad;
   int ntile, nwork;
   int gslot, gst;                // G ring: bytes per slot (7 x rows_max x 32), number of slots
 };
@@ -250,6 +253,7 @@ struct Smem {
 constexpr size_t SMEM_FIXED = (size_t)SST * S_STAGE + VST * V_STAGE + (2 * 2 * NF * 3 + 4 * NF * 3 + NF * 2) * 8 +
                               (8 + 8 + 2 * VST + 2 * SST + 2 + 4) * 8 + 16;
 
+template <bool NMFP>
 __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem sm(smem_raw, ar);
@@ -374,7 +378,16 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
               sm.nval[2 * (c0 + q)] = ys;
               sm.nval[2 * (c0 + q) + 1] = yc;
             }
-            const bool basis = row < pm.m;
+            const bool basis = row < pm.mfix;  // rows of the draw-independent block enter the b-sums (plain Fp: all)
+            if (NMFP && row >= pm.mfix && row < pm.m && f0 + c0 + q < ar.F) {
+              // rows of the per-draw block leave as z' in the layout nmfp_stageB_kernel streams: k-block (row / 4),
+              // column block (4 frequencies), then 16 * {sin, cos} + 4 * (frequency % 4) + row % 4
+              const int jr = row - pm.mfix + (ar.mvpad - pm.mvar), fi = c0 + q;
+              double* z = ar.Z + ((size_t)p * ar.ntile + ft) * ((size_t)ar.mvpad * 64) +
+                          (size_t)(((jr >> 2) * 8 + (fi >> 2)) * 32 + 4 * (fi & 3) + (jr & 3));
+              z[0] = ys;
+              z[16] = yc;
+            }
             v[3 * q] = basis ? ys * ys : 0.0;
             v[3 * q + 1] = basis ? ys * yc : 0.0;
             v[3 * q + 2] = basis ? yc * yc : 0.0;
@@ -442,7 +455,12 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
         const double x1 = (n1 - lq * n0) / u;
         const double x0 = (n0 - m01 * x1) / m00;
         double val = 0.5 * (N0 * x0 + N1 * x1);
-        if (fidx < ar.F) {
+        if (NMFP) {
+          if (fidx < ar.F) {  // the draw-independent pieces (fixed block removed) for stage B
+            double* o = ar.A + ((size_t)p * ar.ntile + ft) * 160 + f;
+            o[0] = a[0] - b[0]; o[32] = a[1] - b[1]; o[64] = a[2] - b[2]; o[96] = N0; o[128] = N1;
+          }
+        } else if (fidx < ar.F) {
           if (!(ar.freqs[fidx] > 0.0)) val = __longlong_as_double(0x7ff8000000000000LL);  // f <= 0: NaN like f**(1/3)
           if (ar.terms) ar.terms[(size_t)p * ar.F + fidx] = val;
           if (ar.inner) {
@@ -632,11 +650,11 @@ int run_i8_peak(int kind, int iters, double* tops, double* ms_out) {
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
-// A pack can take the tensor path when every pulsar fits the tile: diagonal N, plain Fp, m + 1 <= 128 rows (the basis
-// rows and the w row), n <= 16384 TOAs (int32 accumulators: 7 products of |digit|^2 <= 2^14 per TOA stay below 2^31
+// A pack can take the tensor path when every pulsar fits the tile: diagonal N, m + 1 <= 128 rows (the basis rows and
+// the w row), n <= 16384 TOAs (int32 accumulators: 7 products of |digit|^2 <= 2^14 per TOA stay below 2^31
 // up to 18 724 TOAs).
 bool i8_eligible(const fastfp_pack* pk) {
-  if (pk->ecorr || pk->nmfp) return false;
+  if (pk->ecorr) return false;
   for (const PulsarMeta& pm : pk->meta)
     if (pm.m + 1 > 128 || pm.n > 16384) return false;
   return true;
@@ -697,7 +715,7 @@ int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
 }
 
 int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
-                       double* d_inner) {
+                       double* d_inner, const NmfpOut* nm) {
   using namespace i8;
   Args a{};
   a.planes = pk->d_i8;
@@ -708,6 +726,9 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   a.F = F;
   a.terms = d_terms;
   a.inner = d_inner;
+  a.Z = nm ? nm->Z : nullptr;
+  a.A = nm ? nm->A : nullptr;
+  a.mvpad = nm ? nm->mvmax : 0;
   const int64_t ntile = (F + NF - 1) / NF, nwork = ntile * pk->P;
   if (nwork > 0x7fffffffLL) { set_error("frequency batch too large for one launch"); return -1; }
   a.ntile = (int)ntile;
@@ -722,11 +743,13 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   const size_t smem = (size_t)gst * a.gslot + SMEM_FIXED;
   static bool attr_done[64] = {};
   if (!attr_done[pk->device & 63]) {
-    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done[pk->device & 63] = true;
   }
   const unsigned grid = (unsigned)(nwork < pk->num_sms ? nwork : pk->num_sms);
-  fp_sweep_i8_kernel<<<grid, THREADS, smem, st>>>(a);
+  if (nm) fp_sweep_i8_kernel<true><<<grid, THREADS, smem, st>>>(a);
+  else fp_sweep_i8_kernel<false><<<grid, THREADS, smem, st>>>(a);
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
   return 0;

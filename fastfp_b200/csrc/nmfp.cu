@@ -103,6 +103,7 @@ int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res,
     pk->bytes += (int64_t)P * pk->mvpad * (pk->mvpad + 1) * 8;
   }
   cudaFree(d_ur);
+  if (!rc) rc = build_i8_planes(pk, st);  // stage A on the tensor path when every pulsar fits its tile
   return rc;
 }
 
@@ -650,7 +651,10 @@ int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, con
     FFP_CUDA(cudaMemsetAsync(dZ, 0, (size_t)P * nt32 * (MV * 64) * 8, st));
     FFP_CUDA(cudaMemsetAsync(dA, 0, (size_t)P * nt32 * 160 * 8, st));
     NmfpOut nm{dZ, dA, MV};
-    if (int rc = launch_fp_sweep(pk, d_freqs + f0, Fb, nullptr, st, &nm)) return rc;
+    // stage A on the tensor path when the pack carries digit planes, else on the fp64 DMMA kernel
+    const bool i8 = pk->i8_ok && pk->path != FASTFP_PATH_FP64;
+    if (int rc = i8 ? launch_fp_sweep_i8(pk, d_freqs + f0, Fb, nullptr, st, nullptr, &nm)
+                    : launch_fp_sweep(pk, d_freqs + f0, Fb, nullptr, st, &nm)) return rc;
     marks.mark(0, st);
     for (int64_t dd = 0; dd < D; dd += DB) {
       const int Db = (int)std::min(DB, D - dd);

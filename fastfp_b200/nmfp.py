@@ -204,14 +204,19 @@ class NMFP(_PackCache):
 
     :param psrs: objects with ``.toas`` / ``.residuals`` (``nmfp.py:50-51``)
     :param rn_sigs: one :class:`RN_container` per pulsar
-    :param device: CUDA device ordinal (extension; default ``LOCAL_RANK`` or 0)"""
+    :param device: CUDA device ordinal (extension; default ``LOCAL_RANK`` or 0)
+    :param path: kernel of the draw-independent stage A, like :class:`FastFp`'s ``path`` (``"auto"`` / ``"fp64"`` /
+        ``"i8"``; default from ``FASTFP_B200_PATH``)"""
 
-    def __init__(self, psrs, rn_sigs, device=None):
+    def __init__(self, psrs, rn_sigs, device=None, path=None):
         self.psrs = psrs
         self.rn_sigs = rn_sigs
         self.toas = [np.asarray(psr.toas, dtype=np.float64) for psr in psrs]
         self.residuals = [np.asarray(psr.residuals, dtype=np.float64) for psr in psrs]
         self.device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
+        self.path = path if path is not None else os.environ.get("FASTFP_B200_PATH", "auto")
+        if self.path not in ("auto", "fp64", "i8"):
+            raise ValueError("path must be 'auto', 'fp64' or 'i8'")
 
     def __call__(self, fgw, samples, Nvecs, Ts, TNTs):
         return self.calculate_nmfp(fgw, samples, Nvecs, Ts, TNTs)
@@ -242,10 +247,14 @@ class NMFP(_PackCache):
                     f"{m_fix[p]} fixed + {sig.Ffreqs.shape[0]} red-noise entries"
                 )
         if any(blockn.is_block(N) for N in Nvecs):  # block-diagonal N (kernel ECORR)
-            return _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
+            pack = _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
                                             [1.0 / f for f in fixed], device=self.device)
-        return _cabi.Pack.create_nmfp(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
-                                      [1.0 / f for f in fixed], device=self.device)
+        else:
+            pack = _cabi.Pack.create_nmfp(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
+                                          [1.0 / f for f in fixed], device=self.device)
+        if self.path != "auto":
+            pack.set_path(self.path)
+        return pack
 
     def _curn_setup(self):
         flags = {bool(sig.add_curn) for sig in self.rn_sigs}

@@ -73,12 +73,13 @@ int fastfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
 int fastfp_fp_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F, double* out,
                     int flags, void* stream);
 
-/* Which kernel runs the plain-Fp sweep of this pack. Both compute the same statistic to the same parity bar:
+/* Which kernel runs the frequency sweep of this pack (the plain-Fp sweep, the Fe sweep, stage A of nmfp). Both
+ * compute the same quantities to the same parity bar:
  *   FASTFP_PATH_I8    the tensor-core kernel: Y = G [s c] as an error-free product of 8-bit digit planes
  *                     (tcgen05.mma kind::i8, exact int32 accumulation in tensor memory), ~2.5x faster;
  *                     available when every pulsar has m <= 127 basis columns, n <= 16384 TOAs, a diagonal N
  *                     and finite data (fastfp_pack_set_path returns FASTFP_ERR_UNSUPPORTED otherwise);
- *   FASTFP_PATH_FP64  the fp64 DMMA kernel (always available; nmfp and block-N packs use it);
+ *   FASTFP_PATH_FP64  the fp64 DMMA kernel (always available; block-N packs and wide bases use it);
  *   FASTFP_PATH_AUTO  (default) the tensor kernel when available.
  * fastfp_pack_path returns the path in effect (never AUTO). */
 #define FASTFP_PATH_AUTO 0

@@ -73,6 +73,7 @@ def test_c4_shape_bins_do_not_depend_on_their_batch(c4):
     assert abs(2.0 * base.mean() - 2 * pta.P) < 0.15 * 2 * pta.P
 
 
+@pytest.mark.usefixtures("sweep_path")
 def test_c3_shape_nmfp_against_truth():
     """45 x 5000, m = 72, CURN: (draw, bin) entries of the (D, F) result against the truth of the reference
     formula with that draw's Sigma, summed over all 45 pulsars."""

@@ -21,6 +21,7 @@ def _tol(truth_vals, cond):
     return 1e-10 * np.abs(truth_vals) + 256 * EPS * cond
 
 
+@pytest.mark.usefixtures("sweep_path")
 def test_nmfp_matches_reference_goldens(golden):
     g = golden("nmfp")
     samples = _samples(g)
@@ -102,6 +103,7 @@ def _ecorr_case(seed=11):
     return pta, psrs, Ts, TNTs, sigs, phi_args
 
 
+@pytest.mark.usefixtures("sweep_path")
 def test_gp_ecorr_columns_are_eliminated_as_fixed_block():
     pta, psrs, Ts, TNTs, sigs, phi_args = _ecorr_case()
     D, F = 5, 40
@@ -119,6 +121,7 @@ def test_gp_ecorr_columns_are_eliminated_as_fixed_block():
     assert np.abs(got / want - 1).max() < 1e-7
 
 
+@pytest.mark.usefixtures("sweep_path")
 @pytest.mark.parametrize("ncomps,P", [(10, 2), (30, 5), (45, 3)])
 def test_nmfp_against_oracle_shapes(ncomps, P):
     pta = synth.make_pta(P, [300 + 57 * p for p in range(P)], n_tm=[6 + p for p in range(P)], ncomps=ncomps, seed=31)
@@ -150,6 +153,7 @@ def test_nmfp_consistent_with_plain_fp():
     assert np.abs(nm / fp - 1).max() < 1e-5
 
 
+@pytest.mark.usefixtures("sweep_path")
 def test_nmfp_full_size_properties():
     """BASELINE configs[2] shapes (45 pulsars x 5000 TOAs, m = 72): properties that do not need the oracle
     at every bin -- draw batching and draw order do not change a value, a draw equal to the fixed noise
@@ -178,6 +182,7 @@ def test_nmfp_full_size_properties():
     assert np.abs(full[3] / fp - 1).max() < 1e-5
 
 
+@pytest.mark.usefixtures("sweep_path")
 def test_nmfp_mixed_per_draw_widths_in_one_pack():
     """Pulsars with different numbers of red-noise components share one pack: the per-draw blocks are
     padded to the widest one (each at its own top-left offset) and stage B skips a different number of

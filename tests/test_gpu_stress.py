@@ -37,6 +37,7 @@ def test_random_small_fp(seed):
     assert np.all(np.abs(got - tt.astype(float)) <= tol), (P, n_tm, ncomps, ns, F)
 
 
+@pytest.mark.usefixtures("sweep_path")
 @pytest.mark.parametrize("seed", range(12))
 def test_random_small_nmfp(seed):
     rng = np.random.default_rng(2000 + seed)
