@@ -1,9 +1,13 @@
-"""CPU emulation of the round-2 contraction at the level of the statistic: the hoisted
-formulation the CUDA path uses (Sigma = L L^T, G = L^-1 T^T N^-1, w = C^-1 r), with Y = G [s c] computed the way the
-INT8 tensor-core plan would -- signed 7-bit digit planes of G (per-row power-of-two scale), unsigned bit-field digits
-of s/2 + 1/2, exact integer products per digit weight, offset removal, fp64 recombination -- and everything else in
-fp64. It must meet the same envelope against the longdouble truth as the CUDA kernels do on the golden fixture,
-including the ill-conditioned bins next to the red-noise Fourier frequencies. (tools/probes/ holds the GPU side.)"""
+"""CPU emulation of the tensor-core contraction of csrc/fp_sweep_i8.cu at the level of the statistic.
+
+The hoisted formulation the CUDA paths use (Sigma = L L^T, G = L^-1 T^T N^-1, w = C^-1 r) with Y = G [s c] computed
+exactly the way the INT8 kernel does it -- radix-256 balanced digit planes of G (per-row power-of-two scale, |g| < 1/4,
+Qg = rint(g 2^55)) and of sin/cos (Q = rint(x 2^54), the two magic-constant roundings of ``digits7`` reproduced bit for
+bit), planes stored in the SWIZZLE_32B K-major operand layout and read back through it, 28 exact integer plane products
+into 7 accumulators, Horner recombination in fp64, the w row supplying (s|r), (c|r) -- and everything else in fp64. It
+must meet the same envelope against the longdouble truth as the CUDA kernels do on the golden fixtures, including the
+ill-conditioned bins next to the red-noise Fourier frequencies; and the digit formats' invariants are checked directly.
+"""
 import numpy as np
 import pytest
 from scipy.linalg import solve_triangular
@@ -11,51 +15,89 @@ from scipy.linalg import solve_triangular
 from conftest import term_tolerance
 from oracle import fp_oracle as o
 
-NS, BITS = 8, 7
+NPL, KT = 7, 32
+MAGIC = 6755399441055744.0  # 1.5 * 2^52
+BIAS = 0x0080808080808080
 
 
-def _signed_digits(X, e):
-    r = (X / np.exp2(e)).astype(np.longdouble)  # |r| <= 1/2
-    out = []
-    for i in range(1, NS + 1):
-        w = np.longdouble(2.0) ** (BITS * i)
-        d = np.rint(r * w)
-        out.append(d.astype(np.int64))
-        r = r - d / w
-    return out
+def swz32(r, c):
+    """byte offset of (row, K byte) in a K-major tile with 32-byte rows, SWIZZLE_32B (fp_sweep_i8.cu::swz32)"""
+    r, c = np.asarray(r), np.asarray(c)
+    return (r >> 3) * 256 + (r & 7) * 32 + ((((c >> 4) ^ ((r & 7) >> 2)) & 1) << 4) + (c & 15)
 
 
-def _unsigned_digits(X):
-    """base-128 digits of (x/2 + 1/2) 2^56 for x in [-1, 1]; the first digit may be 128"""
-    q = np.floor((X.astype(np.longdouble) * 0.5 + 0.5) * np.longdouble(2.0) ** 56 + 0.5)
-    out = []
-    for _ in range(NS - 1):
-        hi = np.floor(q / 128)
-        out.append((q - hi * 128).astype(np.int64))
-        q = hi
-    out.append(q.astype(np.int64))
-    return out[::-1]
+def digits7(x):
+    """fp_sweep_i8.cu::digits7 in NumPy: x in [-1, 1] -> (7, ...) int8 balanced digits, most significant first.
+    x * 2^26 and rem * 2^54 are exact scalings, so the fused multiply-adds of the kernel round like these sums."""
+    x = np.asarray(x, dtype=np.float64)
+    t1 = x * 67108864.0 + MAGIC
+    hi = (t1.view(np.int64) & 0xffffffff).astype(np.uint32).view(np.int32).astype(np.int64)  # low word, signed
+    rem = x - (t1 - MAGIC) * (1.0 / 67108864.0)
+    t2 = rem * 18014398509481984.0 + MAGIC
+    U = hi * 268435456 + (t2.view(np.int64) - 0x4338000000000000) + BIAS
+    return np.stack([(((U >> (8 * (6 - p))) & 0xff) ^ 0x80).astype(np.uint8).view(np.int8) for p in range(NPL)])
 
 
-def _split_product(G, S):
-    """Y = G S (m x n times n x k) through digit planes; integer arithmetic is exact, as int32 accumulation is."""
-    e = np.ceil(np.log2(np.abs(G).max(axis=1, keepdims=True))) + 1
-    dG, dS = _signed_digits(G, e), _unsigned_digits(S)
-    assert max(np.abs(d).max() for d in dG) <= 64 and max(d.max() for d in dS) <= 128 and min(d.min() for d in dS) >= 0
-    acc = [np.zeros((G.shape[0], S.shape[1]), dtype=np.int64) for _ in range(NS)]
-    for i in range(NS):
-        for j in range(NS - i):
-            acc[i + j] += dG[i] @ dS[j]
-    assert max(np.abs(a).max() for a in acc) < 2 ** 31  # fits the int32 accumulators of the MMA
-    y = np.zeros(acc[0].shape)
-    for g in range(NS - 1, -1, -1):  # smallest weight first, fp64 as in the epilogue
-        y = y + acc[g].astype(np.float64) * 2.0 ** (-BITS * (g + 2))
-    # offset: every S entry carried +1/2, i.e. (1/2) sum_k g_jk per row, exact from the digits
-    gsum = sum(dG[i].sum(axis=1).astype(np.float64) * 2.0 ** (-BITS * (i + 1)) for i in range(NS - 1, -1, -1))
-    return (y - 0.5 * gsum[:, None]) * np.exp2(e + 1)
+def g_planes(G):
+    """i8_rowscale_kernel + i8_planes_kernel: row exponents (|G / 2^e| < 1/4), digits of rint(G 2^(55 - e))"""
+    mx = np.abs(G).max(axis=1)
+    e = np.where(mx > 0, np.frexp(np.where(mx > 0, mx, 1.0))[1] + 2, 0)
+    Q = np.rint(np.ldexp(G, (55 - e)[:, None])).astype(np.int64)
+    assert np.abs(Q).max() <= 2 ** 53
+    U = (Q + BIAS) ^ BIAS
+    return np.stack([((U >> (8 * (6 - p))) & 0xff).astype(np.uint8).view(np.int8) for p in range(NPL)]), e
 
 
-def _terms(g, product):
+def test_digit_formats_are_exact_representations():
+    rng = np.random.default_rng(0)
+    x = np.concatenate((rng.uniform(-1, 1, 20000), [0.0, 1.0, -1.0, 2.0 ** -60, -2.0 ** -30, 1 - 2.0 ** -53]))
+    d = digits7(x).astype(np.int64)
+    Q = sum(d[p] * 256 ** (6 - p) for p in range(NPL))
+    want = np.array([int(np.rint(np.longdouble(v) * np.longdouble(2.0) ** 54)) for v in x], dtype=np.int64)
+    np.testing.assert_array_equal(Q, want)              # the seven digits ARE rint(x 2^54)
+    assert np.abs(x - Q * 2.0 ** -54).max() <= 2.0 ** -55  # i.e. sin/cos are quantised to within 2^-55
+    G = rng.standard_normal((9, 300)) * 10.0 ** rng.uniform(-3, 3, (9, 1)) * 10.0 ** rng.uniform(-1, 1, (9, 300))
+    planes, e = g_planes(G)
+    Qg = sum(planes[p].astype(np.int64) * 256 ** (6 - p) for p in range(NPL))
+    np.testing.assert_array_equal(Qg, np.rint(np.ldexp(G, (55 - e)[:, None])).astype(np.int64))
+    assert np.abs(np.ldexp(G, -e[:, None])).max() < 0.25 and np.abs(planes[0]).max() <= 33
+
+
+def _tensor_product(G, S):
+    """Y = G S^T-like product (G: m x n, S: n x k) through the kernel's data path, stage by stage."""
+    m, n = G.shape
+    k = S.shape[1]
+    rows = (m + 7) // 8 * 8
+    gp, e = g_planes(G)
+    nst = -(-n // KT)
+    acc = [np.zeros((m, k), dtype=np.int64) for _ in range(NPL)]
+    rr, cc = np.meshgrid(np.arange(rows), np.arange(KT), indexing="ij")
+    offA = swz32(rr, cc)
+    r2, c2 = np.meshgrid(np.arange(k), np.arange(KT), indexing="ij")
+    offB = swz32(r2, c2)
+    for st in range(nst):
+        lo, hi = st * KT, min(n, (st + 1) * KT)
+        A = np.zeros((NPL, rows * KT), dtype=np.int8)   # what the TMA copy lands in shared memory
+        B = np.zeros((NPL, k * KT), dtype=np.int8)      # what the producers store
+        tile = np.zeros((NPL, rows, KT), dtype=np.int8)
+        tile[:, :m, : hi - lo] = gp[:, :, lo:hi]
+        A[:, offA.ravel()] = tile.reshape(NPL, -1)
+        stile = np.zeros((NPL, k, KT), dtype=np.int8)
+        stile[:, :, : hi - lo] = digits7(S[lo:hi].T)
+        B[:, offB.ravel()] = stile.reshape(NPL, -1)
+        a = A[:, offA].astype(np.int64)[:, :m]          # what the MMA reads back through the descriptor layout
+        b = B[:, offB].astype(np.int64)
+        for i in range(NPL):
+            for j in range(NPL - i):
+                acc[i + j] += a[i] @ b[j].T
+    assert max(np.abs(x).max() for x in acc) < 2 ** 31  # fits the int32 accumulators in tensor memory
+    y = acc[NPL - 1].astype(np.float64)
+    for g in range(NPL - 2, -1, -1):                    # the epilogue's Horner recombination, smallest weight first
+        y = y * 0.00390625 + acc[g].astype(np.float64)
+    return y * np.exp2(e - 13.0)[:, None]
+
+
+def _terms(g, tensor):
     freqs = g["freqs"]
     out = np.zeros((len(g.psrs), len(freqs)))
     for p, (q, Nvec, T, sigma) in enumerate(zip(g.psrs, g.lst("Nvec"), g.lst("T"), g.lst("sigma"))):
@@ -65,29 +107,36 @@ def _terms(g, product):
         w = r / Nvec - G.T @ (G @ r)
         ph = (2 * np.pi * freqs)[None, :] * t[:, None]  # ((2 pi) f) t, reference rounding order
         s, c = np.sin(ph), np.cos(ph)
-        Y = product(G, np.concatenate((s, c), axis=1))
-        Ys, Yc = Y[:, : len(freqs)], Y[:, len(freqs):]
+        S = np.concatenate((s, c), axis=1)
         ninv = (1.0 / Nvec)[:, None]
+        if tensor:  # rows of G plus the w row through the digit planes
+            Y = _tensor_product(np.concatenate((G, w[None, :]), axis=0), S)
+            n0, n1 = Y[-1, : len(freqs)], Y[-1, len(freqs):]
+            Y = Y[:-1]
+        else:
+            Y = G @ S
+            n0, n1 = (s * w[:, None]).sum(0), (c * w[:, None]).sum(0)
+        Ys, Yc = Y[:, : len(freqs)], Y[:, len(freqs):]
         m00 = (s * s * ninv).sum(0) - (Ys * Ys).sum(0)
         m01 = (s * c * ninv).sum(0) - (Ys * Yc).sum(0)
         m11 = (c * c * ninv).sum(0) - (Yc * Yc).sum(0)
-        n0, n1 = (s * w[:, None]).sum(0), (c * w[:, None]).sum(0)
         det = m00 * m11 - m01 * m01
         out[p] = 0.5 * (n0 * (m11 * n0 - m01 * n1) + n1 * (m00 * n1 - m01 * n0)) / det
     return out
 
 
 @pytest.mark.parametrize("name", ["fp_white", "fp_red"])
-def test_split_precision_contraction_meets_the_parity_envelope(golden, name):
+def test_tensor_contraction_meets_the_parity_envelope(golden, name):
     g = golden(name)
     ora = o.fp_sweep(g["freqs"], g.lst("toas"), g.lst("res"), g.lst("Nvec"), g.lst("T"), g.lst("sigma"), per_pulsar=True)
     tol = term_tolerance(g["truth_terms"], g["cond"], ora)
-    plain = _terms(g, lambda G, S: G @ S)
-    split = _terms(g, _split_product)
+    plain = _terms(g, tensor=False)
+    split = _terms(g, tensor=True)
     # the emulation harness itself (hoisted formulation in NumPy, plain fp64 product) is inside the envelope ...
     assert np.all(np.abs(plain - g["truth_terms"]) <= 2 * tol)
     # ... and so is the digit-plane product; it is not further from the truth than the plain fp64 product
     assert np.all(np.abs(split - g["truth_terms"]) <= 2 * tol)
     e_split = np.abs(split - g["truth_terms"]) / tol
     e_plain = np.abs(plain - g["truth_terms"]) / tol
+    assert e_split.max() <= max(1.5 * e_plain.max(), 0.25)
     assert np.median(e_split) <= 1.5 * np.median(e_plain) + 1e-3
