@@ -19,7 +19,7 @@ constexpr int CTAS_PER_SM = 1;
 constexpr int CONSUMER_REGS = 120, PRODUCER_REGS = 56;  // setmaxnreg split of the 768 x 80 pool
 constexpr int VST = 16;        // TOA-vector ring depth (t | 1/N | w; TMA -> producer)
 constexpr int FLUSH_TOAS = 512;  // level-1 accumulation block, in TOAs
-constexpr int MAX_M = 320;     // widest basis the sweep kernel handles
+constexpr int MAX_M = 640;     // widest basis the sweep kernel handles (8 warp rows x 10 blocks of 8 rows)
 
 // Sweep configuration. The contraction runs on the fp64 MMA path (mma.sync.m8n8k4.f64): a warp
 // owns NMBW row blocks (8 basis rows each) x NNB column blocks (8 columns = 4 frequencies x

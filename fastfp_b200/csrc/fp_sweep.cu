@@ -15,7 +15,11 @@ bool sweep_config(int m, KernelCfg* c) {
   // measured for m = 72: the MMA warps alone get 5% faster, the 8 producer warps fall behind, net -6%)
   if (m <= 80) { *c = {(m + 7) / 8, 2, 1, 32}; return true; }    // 64 frequencies per CTA
   if (m <= 160) { *c = {(m + 15) / 16, 2, 2, 16}; return true; }  // 32 frequencies per CTA
-  *c = {(m + 31) / 32, 2, 4, 16};                                 // 16 frequencies per CTA (m <= 320)
+  if (m <= 320) { *c = {(m + 31) / 32, 2, 4, 16}; return true; }  // 16 frequencies per CTA
+  // all eight consumer warps along the rows, chunks of 8 TOAs (the G tile of a chunk is 8 x 640 doubles = 40 KB): 8
+  // frequencies per CTA. Real pulsars with many DMX columns land here; the tile is reused across 8 frequencies only, so
+  // this family runs at a lower fraction of the pipe than the narrow ones.
+  *c = {(m + 63) / 64, 2, 8, 8};                                  // m <= 640
   return true;
 }
 
@@ -54,7 +58,8 @@ int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, dou
 #endif
   for (const Group& g : pk->groups) {
     int rc;
-    if (g.cfg.wmw == 4) rc = dispatch_sweep_wide(pk, g, a, nm != nullptr, st);
+    if (g.cfg.wmw == 8) rc = dispatch_sweep_xwide(pk, g, a, nm != nullptr, st);
+    else if (g.cfg.wmw == 4) rc = dispatch_sweep_wide(pk, g, a, nm != nullptr, st);
     else if (g.cfg.wmw == 1 && g.cfg.nnb == 4) rc = dispatch_sweep_w1(pk, g, a, nm != nullptr, st);
     else if (g.cfg.wmw == 1) rc = dispatch_sweep_w2(pk, g, a, nm != nullptr, st);
     else rc = dispatch_sweep_w4(pk, g, a, nm != nullptr, st);

@@ -574,6 +574,7 @@ int dispatch_sweep_w1(const fastfp_pack*, const Group&, const SweepArgs&, bool n
 int dispatch_sweep_w2(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 int dispatch_sweep_w4(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 int dispatch_sweep_wide(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
+int dispatch_sweep_xwide(const fastfp_pack*, const Group&, const SweepArgs&, bool nmfp, cudaStream_t);
 
 #define FFP_SWEEP_CASE(NMBWv, NNBv, WMWv, CIv) FFP_SWEEP_CASE_W(NMBWv, NNBv, WMWv, CIv, 8, 16)
 #define FFP_SWEEP_CASE_W(NMBWv, NNBv, WMWv, CIv, NWCv, NWPv)                                       \

@@ -81,8 +81,8 @@ int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res,
   if (pk->mvar_max < 1) { set_error("nmfp pack: every pulsar needs at least one per-draw column (m_fix < m)"); return FASTFP_ERR_INVALID; }
   for (auto& pm : pk->meta)
     if (pm.mvar < 1) { set_error("nmfp pack: every pulsar needs at least one per-draw column (m_fix < m)"); return FASTFP_ERR_INVALID; }
-  const int nmbv = pk->mvar_max <= 32 ? 4 : pk->mvar_max <= 64 ? 8 : pk->mvar_max <= 96 ? 12 : 0;
-  if (!nmbv) { set_error("nmfp pack: more than 96 per-draw columns (48 Fourier components) is not supported"); return FASTFP_ERR_UNSUPPORTED; }
+  const int nmbv = pk->mvar_max <= 32 ? 4 : pk->mvar_max <= 64 ? 8 : pk->mvar_max <= 96 ? 12 : pk->mvar_max <= 128 ? 16 : 0;
+  if (!nmbv) { set_error("nmfp pack: more than 128 per-draw columns (64 Fourier components) is not supported"); return FASTFP_ERR_UNSUPPORTED; }
   pk->mvpad = 8 * nmbv;
   nmfp_init_sigma_kernel<<<P, 256, 0, st>>>(pk->d_L, pk->d_meta, d_TNT, d_phiinv_fix);
   g_launches += 1;
@@ -226,7 +226,7 @@ struct FactorCfg {
   static constexpr int NBLK = NMBV * (NMBV + 1) / 2;
   static constexpr int WSZ = NBLK * 64 + MV;                       // doubles per warp: blocks + z'_r
   static constexpr int FW = NMBV <= 4 ? 8 : NMBV <= 8 ? 4 : 2;     // matrices (warps) per CTA
-  static constexpr int CTAS = NMBV <= 4 ? 4 : NMBV <= 8 ? 3 : 2;   // resident CTAs per SM aimed at
+  static constexpr int CTAS = NMBV <= 4 ? 4 : NMBV <= 8 ? 3 : NMBV <= 12 ? 2 : 1;   // resident CTAs per SM aimed at
   static constexpr size_t SMEM = (size_t)FW * WSZ * 8;
 };
 
@@ -433,21 +433,23 @@ template <int NMBV>
 struct StageBCfg {
   static constexpr int MV = 8 * NMBV, ZT = MV * 64;
   static constexpr int NH = NMBV <= 8 ? 2 : 1;                 // 32-frequency half-tiles per CTA
-  static constexpr int NS = NMBV <= 8 ? 4 : 3;                 // L^-1 ring depth
+  static constexpr int NS = NMBV <= 8 ? 4 : NMBV <= 12 ? 3 : 2;  // L^-1 ring depth
+  static constexpr int ZBUF = NMBV <= 12 ? 2 : 1;              // z' tile buffers (128 columns: one 64 KB tile fits)
   static constexpr int NWB = 8 * NH;                           // consumer warps
   static constexpr int THREADS = 32 * (NWB + 1);
   static constexpr int LFW = (NMBV * (NMBV + 1)) * 32 + MV;    // linv_blocks(NMBV) * 32 + MV
-  static constexpr size_t SMEM = (size_t)(2 * NH * ZT + 2 * NH * 160 + NS * LFW) * 8 + (size_t)(4 + 2 * NS) * 8;
+  static constexpr size_t SMEM = (size_t)(ZBUF * NH * ZT + ZBUF * NH * 160 + NS * LFW) * 8 + (size_t)(4 + 2 * NS) * 8;
+  static_assert(SMEM <= 227 * 1024, "stage B shared memory");
 };
 
 template <int NMBV>
 __global__ void __launch_bounds__(StageBCfg<NMBV>::THREADS, 1) nmfp_stageB_kernel(const StageBArgs ar) {
   using C = StageBCfg<NMBV>;
-  constexpr int KBV = 2 * NMBV, ZT = C::ZT, NH = C::NH, NS = C::NS, NWB = C::NWB, LFW = C::LFW;
+  constexpr int KBV = 2 * NMBV, ZT = C::ZT, NH = C::NH, NS = C::NS, NWB = C::NWB, LFW = C::LFW, ZBUF = C::ZBUF;
   extern __shared__ __align__(128) unsigned char raw[];
-  double* Zb = reinterpret_cast<double*>(raw);       // [2][NH][ZT]
-  double* Ab = Zb + 2 * NH * ZT;                     // [2][NH][160]
-  double* Lb = Ab + 2 * NH * 160;                    // [NS][LFW]
+  double* Zb = reinterpret_cast<double*>(raw);       // [ZBUF][NH][ZT]
+  double* Ab = Zb + ZBUF * NH * ZT;                  // [ZBUF][NH][160]
+  double* Lb = Ab + ZBUF * NH * 160;                 // [NS][LFW]
   uint64_t* zfull = reinterpret_cast<uint64_t*>(Lb + NS * LFW);  // [2]
   uint64_t* zempty = zfull + 2;                                  // [2]
   uint64_t* lfull = zempty + 2;                                  // [NS]
@@ -470,8 +472,8 @@ __global__ void __launch_bounds__(StageBCfg<NMBV>::THREADS, 1) nmfp_stageB_kerne
     for (int it = 0; it < nit; ++it) {
       const int p = it / nd, dl = it - p * nd;
       if (dl == 0) {  // z' tile(s) and the a-terms of pulsar p, before the first L^-1 of that pulsar
-        const int buf = p & 1;
-        if (p >= 2) mbar_wait(&zempty[buf], ((p >> 1) - 1) & 1);
+        const int buf = p % ZBUF;
+        if (p >= ZBUF) mbar_wait(&zempty[buf], ((p / ZBUF) - 1) & 1);
         mbar_expect_tx(&zfull[buf], (uint32_t)(nh * (ZT + 160) * 8));
         tma_load_1d(Zb + buf * NH * ZT, ar.Z + ((size_t)p * ar.nt32 + t32) * ZT, (uint32_t)(nh * ZT * 8),
                     &zfull[buf]);
@@ -503,8 +505,8 @@ __global__ void __launch_bounds__(StageBCfg<NMBV>::THREADS, 1) nmfp_stageB_kerne
   int kb0 = 0;
 
   for (int it = 0; it < nit; ++it) {
-    const int p = it / nd, dl = it - p * nd, buf = p & 1, s = it % NS;
-    if (dl == 0) mbar_wait_spin(&zfull[buf], (p >> 1) & 1);
+    const int p = it / nd, dl = it - p * nd, buf = p % ZBUF, s = it % NS;
+    if (dl == 0) mbar_wait_spin(&zfull[buf], (p / ZBUF) & 1);
     mbar_wait_spin(&lfull[s], (it / NS) & 1);
     const double* zt = Zb + (buf * NH + h) * ZT + wl * 32 + bperm;
     const double* lt = Lb + s * LFW;
@@ -663,7 +665,8 @@ int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, con
       int rc;
       if (NMBV == 4) rc = run_factor_and_stageB<4>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
       else if (NMBV == 8) rc = run_factor_and_stageB<8>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
-      else rc = run_factor_and_stageB<12>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
+      else if (NMBV == 12) rc = run_factor_and_stageB<12>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
+      else rc = run_factor_and_stageB<16>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
       if (rc) return rc;
     }
   }

@@ -73,12 +73,14 @@ def test_get_xcy_general_sigma_uses_pivoted_lu():
     assert abs(fastfp_b200.get_xCy(Nvec, T, sigma, x, y) - want) < 1e-9 * abs(want) + 1e-9
 
 
-# every kernel configuration family: m <= 40, <= 80, <= 160, <= 256 (fp_sweep.cu::sweep_config)
-@pytest.mark.parametrize("n_tm,ncomps", [(2, 0), (5, 3), (12, 30), (20, 30), (9, 45), (40, 55), (150, 45), (230, 40)])
+# every kernel configuration family: m <= 40, <= 80, <= 160, <= 320, <= 640 (fp_sweep.cu::sweep_config)
+@pytest.mark.parametrize("n_tm,ncomps", [(2, 0), (5, 3), (12, 30), (20, 30), (9, 45), (40, 55), (150, 45), (230, 40),
+                                         (340, 30), (500, 60)])
 def test_every_kernel_family_against_oracle(n_tm, ncomps):
     m_ = n_tm + 2 * ncomps
     # ragged, not multiples of the chunk size; comfortably more TOAs than basis columns
-    ns = [333, 64, 1000] if m_ <= 40 else ([333, 300, 1000] if m_ <= 160 else [2500, 1801, 3000])
+    ns = [333, 64, 1000] if m_ <= 40 else ([333, 300, 1000] if m_ <= 160 else ([2500, 1801, 3000] if m_ <= 320
+                                                                          else [4000, 3001, 5000]))
     if ncomps == 0:
         pta = synth.make_pta(3, ns, n_tm=n_tm, white_only=True, seed=77)
     else:

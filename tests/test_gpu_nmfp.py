@@ -122,7 +122,7 @@ def test_gp_ecorr_columns_are_eliminated_as_fixed_block():
 
 
 @pytest.mark.usefixtures("sweep_path")
-@pytest.mark.parametrize("ncomps,P", [(10, 2), (30, 5), (45, 3)])
+@pytest.mark.parametrize("ncomps,P", [(10, 2), (30, 5), (45, 3), (60, 2), (64, 2)])
 def test_nmfp_against_oracle_shapes(ncomps, P):
     pta = synth.make_pta(P, [300 + 57 * p for p in range(P)], n_tm=[6 + p for p in range(P)], ncomps=ncomps, seed=31)
     D, F = 11, 45  # not multiples of the draw tile (8) or the frequency tile (32)
@@ -214,5 +214,24 @@ def test_nmfp_mixed_per_draw_widths_in_one_pack():
         pars = {k: v[d] for k, v in samples.items()}
         sig = o.get_sigmas(pars, TNTs, phi_args)
         tt, cond = truth.fp_sweep_truth(freqs, toas, res, Nvecs, Ts, sig)
+        tv = tt.sum(0).astype(float)
+        assert np.all(np.abs(got[d] - tv) <= _tol(tv, cond.sum(0))), d
+
+
+def test_nmfp_wide_timing_model_block():
+    """Basis wider than 320 columns (many timing-model / DMX columns): the draw-independent
+    block is eliminated once per pulsar as usual, the sweep runs on the 640-row kernel family."""
+    pta = synth.make_pta(2, [2600, 3001], n_tm=[330, 400], ncomps=12, seed=19)
+    assert [T.shape[1] for T in pta.Ts] == [354, 424]
+    D, F = 3, 21
+    samples = synth.draw_samples(pta, D)
+    freqs = np.concatenate((synth.nmfp_freqs(4, pta.Tspan), synth.fp_freqs(F - 4)))
+    sigs = [RN_container(q, Ffreqs=pta.Ffreqs) for q in pta.psrs]
+    got = NMFP(pta.psrs, sigs)(freqs, samples, pta.Nvecs, pta.Ts, pta.TNTs)
+    phi_args = [dict(psr_name=q.name, n_tm=pta.n_tm[p], Ffreqs=pta.Ffreqs) for p, q in enumerate(pta.psrs)]
+    for d in (0, D - 1):
+        pars = {k: v[d] for k, v in samples.items()}
+        sig = o.get_sigmas(pars, pta.TNTs, phi_args)
+        tt, cond = truth.fp_sweep_truth(freqs, pta.toas, pta.residuals, pta.Nvecs, pta.Ts, sig)
         tv = tt.sum(0).astype(float)
         assert np.all(np.abs(got[d] - tv) <= _tol(tv, cond.sum(0))), d
