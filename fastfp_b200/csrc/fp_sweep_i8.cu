@@ -668,7 +668,10 @@ int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
   int64_t off = 0;
   int rows_max = 0, nst_max = 0;
   for (PulsarMeta& pm : pk->meta) {
-    pm.i8_rows = (pm.m + 1 + 7) / 8 * 8;
+    // rows padded to 32: every plane then starts on a 1024-byte boundary of the (1024-aligned) ring, the alignment
+    // the operand descriptors of all swizzle modes accept; rows beyond the padding are never loaded (the MMA reads
+    // 128 rows per plane, the tail comes from the next plane and lands in output lanes nobody reads)
+    pm.i8_rows = (pm.m + 1 + 31) / 32 * 32;
     pm.i8_nst = (pm.n + i8::KT - 1) / i8::KT;
     pm.i8_off = off;
     off += (int64_t)pm.i8_nst * (i8::V_STAGE + i8::NPL * pm.i8_rows * i8::KT);
