@@ -232,8 +232,7 @@ int fastfp_pack_set_path(fastfp_pack_t* pk, int path) {
 
 int fastfp_pack_path(const fastfp_pack_t* pk) {
   if (!pk) return FASTFP_ERR_INVALID;
-  if (pk->path == FASTFP_PATH_AUTO) return pk->i8_ok ? FASTFP_PATH_I8 : FASTFP_PATH_FP64;
-  return pk->path;
+  return pk->use_i8() ? FASTFP_PATH_I8 : FASTFP_PATH_FP64;
 }
 
 int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
@@ -372,7 +371,7 @@ static const int64_t kTermBudgetDoubles = 1LL << 27;  // 1 GiB
 // per-pulsar terms of one frequency batch on the path the pack is set to
 static int sweep_terms(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
                        double* d_inner = nullptr) {
-  const bool i8 = pk->i8_ok && pk->path != FASTFP_PATH_FP64;
+  const bool i8 = pk->use_i8();
   return i8 ? launch_fp_sweep_i8(pk, d_freqs, F, d_terms, st, d_inner)
             : launch_fp_sweep(pk, d_freqs, F, d_terms, st, nullptr, d_inner);
 }

@@ -654,7 +654,7 @@ int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, con
     FFP_CUDA(cudaMemsetAsync(dA, 0, (size_t)P * nt32 * 160 * 8, st));
     NmfpOut nm{dZ, dA, MV};
     // stage A on the tensor path when the pack carries digit planes, else on the fp64 DMMA kernel
-    const bool i8 = pk->i8_ok && pk->path != FASTFP_PATH_FP64;
+    const bool i8 = pk->use_i8();
     if (int rc = i8 ? launch_fp_sweep_i8(pk, d_freqs + f0, Fb, nullptr, st, nullptr, &nm)
                     : launch_fp_sweep(pk, d_freqs + f0, Fb, nullptr, st, &nm)) return rc;
     marks.mark(0, st);

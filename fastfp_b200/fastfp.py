@@ -140,8 +140,8 @@ class FastFp(_PackCache):
         import os as _os
 
         self.path = path if path is not None else _os.environ.get("FASTFP_B200_PATH", "auto")
-        if self.path not in ("auto", "fp64", "i8"):
-            raise ValueError("path must be 'auto', 'fp64' or 'i8'")
+        if self.path not in ("auto", "fp64", "i8", "prefer-i8"):
+            raise ValueError("path must be 'auto', 'fp64', 'i8' or 'prefer-i8'")
 
     # -- packing (one-time, frequency-independent precompute on the device) -----------------
     def _build_pack(self, lists):
@@ -152,7 +152,12 @@ class FastFp(_PackCache):
             pack = _cabi.Pack.create_blockn(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
         else:
             pack = _cabi.Pack.create_fp(self.toas, self.residuals, Nvecs, Ts, sigmas, device=self.device)
-        if self.path != "auto":
+        if self.path == "prefer-i8":  # the tensor kernel where the pack can take it, silently the fp64 one otherwise
+            try:
+                pack.set_path("i8")
+            except _cabi.FastFpError:
+                pass
+        elif self.path != "auto":
             pack.set_path(self.path)
         return pack
 

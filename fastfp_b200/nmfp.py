@@ -215,8 +215,8 @@ class NMFP(_PackCache):
         self.residuals = [np.asarray(psr.residuals, dtype=np.float64) for psr in psrs]
         self.device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
         self.path = path if path is not None else os.environ.get("FASTFP_B200_PATH", "auto")
-        if self.path not in ("auto", "fp64", "i8"):
-            raise ValueError("path must be 'auto', 'fp64' or 'i8'")
+        if self.path not in ("auto", "fp64", "i8", "prefer-i8"):
+            raise ValueError("path must be 'auto', 'fp64', 'i8' or 'prefer-i8'")
 
     def __call__(self, fgw, samples, Nvecs, Ts, TNTs):
         return self.calculate_nmfp(fgw, samples, Nvecs, Ts, TNTs)
@@ -252,7 +252,12 @@ class NMFP(_PackCache):
         else:
             pack = _cabi.Pack.create_nmfp(self.toas, self.residuals, Nvecs, Ts, TNTs, m_fix,
                                           [1.0 / f for f in fixed], device=self.device)
-        if self.path != "auto":
+        if self.path == "prefer-i8":  # the tensor kernel where the pack can take it, silently the fp64 one otherwise
+            try:
+                pack.set_path("i8")
+            except _cabi.FastFpError:
+                pass
+        elif self.path != "auto":
             pack.set_path(self.path)
         return pack
 
