@@ -766,7 +766,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--sweep-path", choices=["auto", "fp64", "i8"], default=None,
+    ap.add_argument("--sweep-path", choices=["auto", "fp64", "i8", "prefer-i8"], default=None,
                     help="kernel of the plain-Fp sweep (default auto: the INT8 tensor-core kernel when the pack fits it)")
     args = ap.parse_args()
     if args.steps < 1:

@@ -84,4 +84,82 @@ FFP_HD void sincos_cw(double x, double* sp, double* cp) {
 #endif
 }
 
+// NV evaluations of sincos_cw in lockstep: the same operations per element in the same order (bit-identical results),
+// written step by step over the NV arguments so that the independent chains are adjacent in the instruction stream
+// (the polynomial constants are materialised once per step, and the scheduler has NV-way parallelism to hide the
+// fp64 latency) -- the producers of the tensor-core sweep evaluate four (TOA, frequency) pairs per thread and stage.
+template <int NV>
+FFP_HD void sincos_cw_n(const double (&x)[NV], double (&sp)[NV], double (&cp)[NV]) {
+  const double magic = 6755399441055744.0;
+  double kd[NV], k[NV], r[NV], z[NV], ps[NV], pc[NV];
+  int q[NV];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) kd[e] = ffp_fma(x[e], 0.6366197723675814, magic);
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+#if defined(__CUDA_ARCH__)
+    q[e] = __double2loint(kd[e]);
+#else
+    int64_t bits;
+    std::memcpy(&bits, &kd[e], 8);
+    q[e] = (int)(uint32_t)bits;
+#endif
+    k[e] = kd[e] - magic;
+  }
+#pragma unroll
+  for (int e = 0; e < NV; ++e) r[e] = ffp_fma(-k[e], 1.5707963267948966, x[e]);
+#pragma unroll
+  for (int e = 0; e < NV; ++e) r[e] = ffp_fma(-k[e], 6.123233995736766e-17, r[e]);
+#pragma unroll
+  for (int e = 0; e < NV; ++e) r[e] = ffp_fma(-k[e], -1.4973849048591698e-33, r[e]);
+#pragma unroll
+  for (int e = 0; e < NV; ++e) z[e] = r[e] * r[e];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    ps[e] = ffp_fma(z[e], 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    pc[e] = ffp_fma(z[e], -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  }
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    ps[e] = ffp_fma(z[e], ps[e], 2.75573137070700676789e-06);
+    pc[e] = ffp_fma(z[e], pc[e], -2.75573143513906633035e-07);
+  }
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    ps[e] = ffp_fma(z[e], ps[e], -1.98412698298579493134e-04);
+    pc[e] = ffp_fma(z[e], pc[e], 2.48015872894767294178e-05);
+  }
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    ps[e] = ffp_fma(z[e], ps[e], 8.33333333332248946124e-03);
+    pc[e] = ffp_fma(z[e], pc[e], -1.38888888888741095749e-03);
+  }
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    ps[e] = ffp_fma(z[e], ps[e], -1.66666666666666324348e-01);
+    pc[e] = ffp_fma(z[e], pc[e], 4.16666666666666019037e-02);
+  }
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    const double s = ffp_fma(r[e] * z[e], ps[e], r[e]);
+    const double c = ffp_fma(z[e], ffp_fma(z[e], pc[e], -0.5), 1.0);
+    const bool swap = (q[e] & 1) != 0;
+    const double so = swap ? c : s;
+    const double co = swap ? s : c;
+    const uint32_t fs = ((uint32_t)q[e] & 2u) << 30, fc = ((uint32_t)(q[e] + 1) & 2u) << 30;
+#if defined(__CUDA_ARCH__)
+    sp[e] = __hiloint2double(__double2hiint(so) ^ (int)fs, __double2loint(so));
+    cp[e] = __hiloint2double(__double2hiint(co) ^ (int)fc, __double2loint(co));
+#else
+    uint64_t bs, bc;
+    std::memcpy(&bs, &so, 8);
+    std::memcpy(&bc, &co, 8);
+    bs ^= (uint64_t)fs << 32;
+    bc ^= (uint64_t)fc << 32;
+    std::memcpy(&sp[e], &bs, 8);
+    std::memcpy(&cp[e], &bc, 8);
+#endif
+  }
+}
+
 }  // namespace ffp

@@ -30,6 +30,7 @@
 // tools/probes/umma_i8_shape_probe.cu), i.e. 1344 cycles per stage against ~3490 for the same work on the DMMA path.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/fastfp_b200.h"
 #include "ffp_internal.cuh"
@@ -46,10 +47,18 @@ constexpr int S_PLANE = NBR * KT;      // 2048 bytes
 constexpr int S_STAGE = NPL * S_PLANE; // 14336 bytes
 constexpr int V_STAGE = KT * 16;       // (t, 1/N) per TOA
 constexpr int SST = 6, VST = 8;        // ring depths (even: a slot is always served by the same producer group)
-constexpr int THREADS = 768;
-constexpr int NPW = 16;                // producer warps
-constexpr int REGS_LAUNCH = 80, REGS_CTRL = 56, REGS_EPI = 136, REGS_PROD = 72;
-static_assert(128 * REGS_CTRL + 128 * REGS_EPI + 512 * REGS_PROD <= THREADS * REGS_LAUNCH, "register pool");
+// Warp layout: warps 0-3 control (TMA, MMA issue), 4-7 epilogue, 8.. producers. A stage is always produced by 8
+// warps (thread = one frequency x four TOAs); with NPW = 16 two groups of 8 alternate stages, with NPW = 8 one group
+// takes every stage and each producer thread gets twice the registers.
+template <int NPW>
+struct Roles {
+  static_assert(NPW == 8 || NPW == 16, "8 or 16 producer warps");
+  static constexpr int THREADS = 256 + 32 * NPW;
+  static constexpr int NG = NPW / 8;                                   // producer groups
+  static constexpr int REGS_LAUNCH = NPW == 16 ? 80 : 128;             // 65536 / THREADS, multiple of 8
+  static constexpr int REGS_CTRL = 56, REGS_EPI = 136, REGS_PROD = NPW == 16 ? 72 : 152;
+  static_assert(128 * REGS_CTRL + 128 * REGS_EPI + 32 * NPW * REGS_PROD <= THREADS * REGS_LAUNCH, "register pool");
+};
 static_assert(SST % 2 == 0 && VST % 2 == 0, "ring depths must be even");
 
 struct Args {
@@ -221,11 +230,9 @@ __device__ __forceinline__ void wait_wd(uint64_t* bar, uint32_t parity, int tag,
   }
 }
 
-__device__ __noinline__ void sincos_library(double ph, double* s, double* c) { sincos(ph, s, c); }
-
 struct Smem {
   unsigned char *G, *S, *V;
-  double *redA;          // [2][2][NF][3] producer sums: buffer, producer group, frequency
+  double *redA;          // [2][2][NF][3] producer sums: buffer, producer group (one or two), frequency
   double *part;          // [4][NF][3]    epilogue partial b-sums per warp
   double *nval;          // [NF][2]       (s|r), (c|r) from the w row
   uint64_t *g_full, *g_empty, *v_full, *v_empty, *s_full, *s_empty, *acc_full, *acc_empty, *sums_full, *sums_empty;
@@ -253,15 +260,17 @@ struct Smem {
 constexpr size_t SMEM_FIXED = (size_t)SST * S_STAGE + VST * V_STAGE + (2 * 2 * NF * 3 + 4 * NF * 3 + NF * 2) * 8 +
                               (8 + 8 + 2 * VST + 2 * SST + 2 + 4) * 8 + 16;
 
-template <bool NMFP>
-__global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) {
+template <bool NMFP, int NPW>
+__global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(const Args ar) {
+  using R = Roles<NPW>;
+  constexpr int NG = R::NG;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem sm(smem_raw, ar);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) {
     for (int s = 0; s < ar.gst; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], 1); }
-    for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], NPW / 2); }
-    for (int s = 0; s < SST; ++s) { mbar_init(&sm.s_full[s], NPW / 2); mbar_init(&sm.s_empty[s], 1); }
+    for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 8); }
+    for (int s = 0; s < SST; ++s) { mbar_init(&sm.s_full[s], 8); mbar_init(&sm.s_empty[s], 1); }
     mbar_init(sm.acc_full, 1);
     mbar_init(sm.acc_empty, 4);
     for (int b = 0; b < 2; ++b) { mbar_init(&sm.sums_full[b], NPW); mbar_init(&sm.sums_empty[b], 1); }
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
 
   if (wid < 4) {
     // ================= control warpgroup: TMA (warp 0) and MMA issue (warp 1) =================
-    reg_set_dec<REGS_CTRL>();
+    reg_set_dec<R::REGS_CTRL>();
     if (wid == 0 && lane == 0) {
       uint32_t k = 0;
       for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x) {
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
     }
   } else if (wid < 8) {
     // ================= epilogue warpgroup: one TMEM lane quarter per warp =================
-    reg_set_inc<REGS_EPI>();
+    reg_set_inc<R::REGS_EPI>();
     const int ew = wid - 4;
     const int row = 32 * ew + lane;
     uint32_t it = 0;
@@ -439,8 +448,10 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
 #pragma unroll
           for (int k2 = 0; k2 < 3; ++k2) b[k2] += sm.part[((size_t)w2 * NF + f) * 3 + k2];
 #pragma unroll
-        for (int k2 = 0; k2 < 3; ++k2)
-          a[k2] = sm.redA[((buf * 2 + 0) * NF + f) * 3 + k2] + sm.redA[((buf * 2 + 1) * NF + f) * 3 + k2];
+        for (int k2 = 0; k2 < 3; ++k2) {
+          a[k2] = sm.redA[((buf * 2 + 0) * NF + f) * 3 + k2];
+          if (NG == 2) a[k2] += sm.redA[((buf * 2 + 1) * NF + f) * 3 + k2];
+        }
         const double N0 = sm.nval[2 * f], N1 = sm.nval[2 * f + 1];
         // M = [[ss, sc],[sc, cc]], N = [n0, n1]; LU with partial pivoting
         double m00 = a[0] - b[0], m01 = a[1] - b[1], m10 = m01, m11 = a[2] - b[2];
@@ -475,10 +486,13 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
     }
   } else {
     // ================= producers: sin/cos digit planes + the three quadratic sums =================
-    reg_set_dec<REGS_PROD>();
+    if (NPW == 16) reg_set_dec<R::REGS_PROD>();
+    else reg_set_inc<R::REGS_PROD>();
     const int pw = wid - 8;
-    const uint32_t grp = (uint32_t)(pw >> 3);          // serves the stages with (global stage index & 1) == grp
-    const int fl = lane >> 3, kg = lane & 7;
+    const uint32_t grp = (uint32_t)(pw >> 3);          // serves the stages with (global stage index % NG) == grp
+    // lane = 4 * kg + fl: the 8 lanes of a quarter-warp read two distinct (t, 1/N) entries 64 bytes apart (no bank
+    // conflict on the 16-byte loads), and a warp's 4-byte stores cover 4 rows x 32 bytes = all 32 banks
+    const int kg = lane >> 2, fl = lane & 3;
     const int f = 4 * (pw & 7) + fl;                   // frequency inside the tile
     const int soff = swz32(f, 4 * kg);                 // word of TOAs 4kg..4kg+3 in row f (sin); cos row: + 1024
     uint32_t kbase = 0, it = 0;
@@ -491,55 +505,85 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
       const bool fast = __all_sync(0xffffffffu, fabs(omega) * pm.tabs_max <= 0.999 * FFP_SINCOS_MAX);
       double s3[3] = {0.0, 0.0, 0.0};
       const int nst = pm.i8_nst;
-      for (int c = (int)((kbase ^ grp) & 1u); c < nst; c += 2) {
+      const int c0 = NG == 1 ? 0 : (int)((kbase ^ grp) & 1u);
+      for (int c = c0; c < nst; c += NG) {
         const uint32_t k = kbase + (uint32_t)c;
         const uint32_t sv = k % VST, ss = k % SST;
         wait_wd(&sm.v_full[sv], (k / VST) & 1u, 8, k, false);
         if (k >= SST) wait_wd(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k, false);
         const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
-        uint32_t slo[4], shi[4], clo[4], chi[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double2 tn = vv[e];                      // (t, 1/N)
-          const double ph = __dmul_rn(omega, tn.x);      // ((2*pi)*f)*t, rounded once more
-          double s, cs;
-          if (fast) sincos_cw(ph, &s, &cs);
-          else sincos_library(ph, &s, &cs);              // beyond the Cody-Waite range (or NaN/Inf): library path
-          const double sn = s * tn.y, cn = cs * tn.y;
-          s3[0] = fma(sn, s, s3[0]);
-          s3[1] = fma(sn, cs, s3[1]);
-          s3[2] = fma(cn, cs, s3[2]);
-          const uint2 ds = digits7(s), dc = digits7(cs);
-          slo[e] = ds.x; shi[e] = ds.y; clo[e] = dc.x; chi[e] = dc.y;
-        }
-        // 4 x 7 byte transpose: word of plane p (most significant first) = byte (6 - p) of the four values
         unsigned char* sb = sm.S + ss * S_STAGE + soff;
-        {
-          const uint32_t a = __byte_perm(slo[0], slo[1], 0x5140), b = __byte_perm(slo[0], slo[1], 0x7362);
-          const uint32_t c2 = __byte_perm(slo[2], slo[3], 0x5140), d = __byte_perm(slo[2], slo[3], 0x7362);
-          const uint32_t e2 = __byte_perm(shi[0], shi[1], 0x5140), f2 = __byte_perm(shi[0], shi[1], 0x7362);
-          const uint32_t g2 = __byte_perm(shi[2], shi[3], 0x5140), h2 = __byte_perm(shi[2], shi[3], 0x7362);
-          *reinterpret_cast<uint32_t*>(sb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);   // byte 0
-          *reinterpret_cast<uint32_t*>(sb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);   // byte 1
-          *reinterpret_cast<uint32_t*>(sb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);    // byte 2
-          *reinterpret_cast<uint32_t*>(sb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);    // byte 3
-          *reinterpret_cast<uint32_t*>(sb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);  // byte 4
-          *reinterpret_cast<uint32_t*>(sb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);  // byte 5
-          *reinterpret_cast<uint32_t*>(sb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);  // byte 6
-        }
-        {
-          unsigned char* cb = sb + NF * KT;  // cos rows 32..63
-          const uint32_t a = __byte_perm(clo[0], clo[1], 0x5140), b = __byte_perm(clo[0], clo[1], 0x7362);
-          const uint32_t c2 = __byte_perm(clo[2], clo[3], 0x5140), d = __byte_perm(clo[2], clo[3], 0x7362);
-          const uint32_t e2 = __byte_perm(chi[0], chi[1], 0x5140), f2 = __byte_perm(chi[0], chi[1], 0x7362);
-          const uint32_t g2 = __byte_perm(chi[2], chi[3], 0x5140), h2 = __byte_perm(chi[2], chi[3], 0x7362);
-          *reinterpret_cast<uint32_t*>(cb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);
-          *reinterpret_cast<uint32_t*>(cb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);
-          *reinterpret_cast<uint32_t*>(cb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);
-          *reinterpret_cast<uint32_t*>(cb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);
-          *reinterpret_cast<uint32_t*>(cb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);
-          *reinterpret_cast<uint32_t*>(cb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);
-          *reinterpret_cast<uint32_t*>(cb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);
+        if (fast) {
+          // four (TOA, frequency) pairs in lockstep: phases inside the Cody-Waite range (checked once per item)
+          double ph[4], ninv[4], sv4[4], cv4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double2 tn = vv[e];                    // (t, 1/N)
+            ph[e] = __dmul_rn(omega, tn.x);              // ((2*pi)*f)*t, rounded once more
+            ninv[e] = tn.y;
+          }
+          sincos_cw_n<4>(ph, sv4, cv4);
+          uint32_t slo[4], shi[4], clo[4], chi[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double sn = sv4[e] * ninv[e], cn = cv4[e] * ninv[e];
+            s3[0] = fma(sn, sv4[e], s3[0]);
+            s3[1] = fma(sn, cv4[e], s3[1]);
+            s3[2] = fma(cn, cv4[e], s3[2]);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint2 ds = digits7(sv4[e]), dc = digits7(cv4[e]);
+            slo[e] = ds.x; shi[e] = ds.y; clo[e] = dc.x; chi[e] = dc.y;
+          }
+          // 4 x 7 byte transpose: word of plane p (most significant first) = byte (6 - p) of the four values
+          {
+            const uint32_t a = __byte_perm(slo[0], slo[1], 0x5140), b = __byte_perm(slo[0], slo[1], 0x7362);
+            const uint32_t c2 = __byte_perm(slo[2], slo[3], 0x5140), d = __byte_perm(slo[2], slo[3], 0x7362);
+            const uint32_t e2 = __byte_perm(shi[0], shi[1], 0x5140), f2 = __byte_perm(shi[0], shi[1], 0x7362);
+            const uint32_t g2 = __byte_perm(shi[2], shi[3], 0x5140), h2 = __byte_perm(shi[2], shi[3], 0x7362);
+            *reinterpret_cast<uint32_t*>(sb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);   // byte 0
+            *reinterpret_cast<uint32_t*>(sb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);   // byte 1
+            *reinterpret_cast<uint32_t*>(sb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);    // byte 2
+            *reinterpret_cast<uint32_t*>(sb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);    // byte 3
+            *reinterpret_cast<uint32_t*>(sb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);  // byte 4
+            *reinterpret_cast<uint32_t*>(sb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);  // byte 5
+            *reinterpret_cast<uint32_t*>(sb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);  // byte 6
+          }
+          {
+            unsigned char* cb = sb + NF * KT;  // cos rows 32..63
+            const uint32_t a = __byte_perm(clo[0], clo[1], 0x5140), b = __byte_perm(clo[0], clo[1], 0x7362);
+            const uint32_t c2 = __byte_perm(clo[2], clo[3], 0x5140), d = __byte_perm(clo[2], clo[3], 0x7362);
+            const uint32_t e2 = __byte_perm(chi[0], chi[1], 0x5140), f2 = __byte_perm(chi[0], chi[1], 0x7362);
+            const uint32_t g2 = __byte_perm(chi[2], chi[3], 0x5140), h2 = __byte_perm(chi[2], chi[3], 0x7362);
+            *reinterpret_cast<uint32_t*>(cb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);
+            *reinterpret_cast<uint32_t*>(cb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);
+            *reinterpret_cast<uint32_t*>(cb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);
+            *reinterpret_cast<uint32_t*>(cb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);
+            *reinterpret_cast<uint32_t*>(cb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);
+            *reinterpret_cast<uint32_t*>(cb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);
+            *reinterpret_cast<uint32_t*>(cb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);
+          }
+        } else {
+          // cold: some phase of this item may exceed the Cody-Waite range (or is NaN/Inf): library sincos, one pair at
+          // a time, digits written byte by byte
+#pragma unroll 1
+          for (int e = 0; e < 4; ++e) {
+            const double2 tn = vv[e];
+            double sv1, cv1;
+            sincos(__dmul_rn(omega, tn.x), &sv1, &cv1);
+            const double sn = sv1 * tn.y, cn = cv1 * tn.y;
+            s3[0] = fma(sn, sv1, s3[0]);
+            s3[1] = fma(sn, cv1, s3[1]);
+            s3[2] = fma(cn, cv1, s3[2]);
+            const uint2 ds = digits7(sv1), dc = digits7(cv1);
+            const unsigned long long us = ((unsigned long long)ds.y << 32) | ds.x, uc = ((unsigned long long)dc.y << 32) | dc.x;
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) {
+              sb[p * S_PLANE + e] = (unsigned char)(us >> (8 * (6 - p)));
+              sb[p * S_PLANE + NF * KT + e] = (unsigned char)(uc >> (8 * (6 - p)));
+            }
+          }
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
@@ -549,13 +593,13 @@ __global__ void __launch_bounds__(THREADS, 1) fp_sweep_i8_kernel(const Args ar) 
         }
       }
       kbase += (uint32_t)nst;
-      // the three sums of frequency f: over the 8 lanes that share it, then published per producer group
+      // the three sums of frequency f: over the 8 lanes that share it (lane bits 2..4), then published per group
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         double t = s3[q];
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        t += __shfl_xor_sync(0xffffffffu, t, 2);
         t += __shfl_xor_sync(0xffffffffu, t, 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 16);
         s3[q] = t;
       }
       const uint32_t buf = it & 1u;
@@ -746,13 +790,22 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   const size_t smem = (size_t)gst * a.gslot + SMEM_FIXED;
   static bool attr_done[64] = {};
   if (!attr_done[pk->device & 63]) {
-    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done[pk->device & 63] = true;
   }
   const unsigned grid = (unsigned)(nwork < pk->num_sms ? nwork : pk->num_sms);
-  if (nm) fp_sweep_i8_kernel<true><<<grid, THREADS, smem, st>>>(a);
-  else fp_sweep_i8_kernel<false><<<grid, THREADS, smem, st>>>(a);
+  // producer warps per CTA: a tuning knob while the kernel is being brought up (both variants compute the same bits)
+  static const int npw = getenv("FASTFP_B200_I8_NPW") ? atoi(getenv("FASTFP_B200_I8_NPW")) : 8;
+  if (npw == 16) {
+    if (nm) fp_sweep_i8_kernel<true, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
+    else fp_sweep_i8_kernel<false, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
+  } else {
+    if (nm) fp_sweep_i8_kernel<true, 8><<<grid, Roles<8>::THREADS, smem, st>>>(a);
+    else fp_sweep_i8_kernel<false, 8><<<grid, Roles<8>::THREADS, smem, st>>>(a);
+  }
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
   return 0;

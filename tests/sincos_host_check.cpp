@@ -25,5 +25,18 @@ int main(int argc, char** argv) {
     if (fabs((double)tc) > 1e-3 && uc > max_ulp) max_ulp = uc;
   }
   printf("max_abs_err %.3e max_ulp_err %.3f worst_x %.17g\n", max_abs, max_ulp, worst_x);
+  // the lockstep form used by the tensor-core sweep's producers must agree with the scalar form bit for bit
+  long mismatch = 0;
+  for (long i = 0; i < N / 4; ++i) {
+    double x[4], s4[4], c4[4];
+    for (int e = 0; e < 4; ++e) x[e] = (i & 1) ? U(rng) : V(rng);
+    ffp::sincos_cw_n<4>(x, s4, c4);
+    for (int e = 0; e < 4; ++e) {
+      double s, c;
+      ffp::sincos_cw(x[e], &s, &c);
+      if (memcmp(&s, &s4[e], 8) || memcmp(&c, &c4[e], 8)) ++mismatch;
+    }
+  }
+  printf("lockstep_mismatch %ld\n", mismatch);
   return 0;
 }

@@ -21,3 +21,5 @@ def test_sincos_cw_accuracy(tmp_path):
     assert m, out
     assert float(m.group(1)) < 2.3e-16  # absolute, over |x| <= 1e5 rad
     assert float(m.group(2)) < 2.0  # ulp, where |value| >= 1e-3
+    m2 = re.search(r"lockstep_mismatch (\d+)", out)
+    assert m2 and int(m2.group(1)) == 0, out  # sincos_cw_n<4> == sincos_cw bit for bit
