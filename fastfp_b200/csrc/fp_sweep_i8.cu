@@ -47,6 +47,7 @@ constexpr int S_PLANE = NBR * KT;      // 2048 bytes
 constexpr int S_STAGE = NPL * S_PLANE; // 14336 bytes
 constexpr int V_STAGE = KT * 16;       // (t, 1/N) per TOA
 constexpr int SST = 6, VST = 8;        // ring depths (even: a slot is always served by the same producer group)
+constexpr int NACC_COLS = NPL * NBR;   // 448 accumulator columns of tensor memory; the TS form keeps 56 more for the G planes
 // Warp layout: warps 0-3 control (TMA, MMA issue), 4-7 epilogue, 8.. producers. A stage is always produced by 8
 // warps (thread = one frequency x four TOAs); with NPW = 16 two groups of 8 alternate stages, with NPW = 8 one group
 // takes every stage and each producer thread gets twice the registers.
@@ -75,6 +76,7 @@ struct Args {
   int mvpad;
   int ntile, nwork;
   int gslot, gst;                // G ring: bytes per slot (7 x rows_max x 32), number of slots
+  int ts;                        // 1: the G planes are copied to tensor memory once per stage and the MMAs take A from there
 };
 
 // byte offset of (row r, K byte c) in a K-major tile with 32-byte rows, SWIZZLE_32B: 8-row groups of 256 bytes, the
@@ -182,6 +184,18 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// A from tensor memory (TS form): lane = row of G, 8 columns hold the row's 32 K-bytes (filled by tmem_cp_plane)
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one digit plane (128 rows x 32 bytes, SWIZZLE_32B K-major in shared memory) -> 128 lanes x 8 columns of TMEM
+__device__ __forceinline__ void tmem_cp_plane(uint32_t tmem_a, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_a), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];\n" ::"l"((uint64_t)smem_u32(bar)) : "memory");
@@ -309,26 +323,60 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NBR >> 3) << 17) | ((128u >> 4) << 24);
       uint32_t k = 0, it = 0;
+      const uint32_t ta = tm + (uint32_t)(NACC_COLS);   // TS form: 7 planes x 8 columns behind the accumulators
+      if (ar.ts && (int)blockIdx.x < ar.nwork) {        // planes of the very first stage
+        const PulsarMeta pm0 = ar.meta[ar.pidx[blockIdx.x / ar.ntile]];
+        wait_wd(&sm.g_full[0], 0u, 4, 0u, true);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) tmem_cp_plane(ta + 8 * i, umma_desc(smem_u32(sm.G) + (uint32_t)(i * pm0.i8_rows * KT)));
+        umma_commit(&sm.g_empty[0]);
+      }
       for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
         const PulsarMeta pm = ar.meta[ar.pidx[item / ar.ntile]];
         const uint32_t aplane = (uint32_t)(pm.i8_rows * KT);
+        const int nitem = item + (int)gridDim.x;
+        const uint32_t aplane_next_item = nitem < ar.nwork ? (uint32_t)(ar.meta[ar.pidx[nitem / ar.ntile]].i8_rows * KT) : 0u;
         if (it > 0) wait_wd(sm.acc_empty, (it - 1) & 1u, 3, it, true);  // the epilogue has drained the accumulators
         for (int c = 0; c < pm.i8_nst; ++c, ++k) {
           const uint32_t sg = k % (uint32_t)ar.gst, ss = k % SST;
-          wait_wd(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k, true);
-          wait_wd(&sm.s_full[ss], (k / SST) & 1u, 5, k, true);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(sm.G + (size_t)sg * ar.gslot), b0 = smem_u32(sm.S + ss * S_STAGE);
+          const uint32_t b0 = smem_u32(sm.S + ss * S_STAGE);
+          if (!ar.ts) {
+            wait_wd(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k, true);
+            wait_wd(&sm.s_full[ss], (k / SST) & 1u, 5, k, true);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sm.G + (size_t)sg * ar.gslot);
 #pragma unroll
-          for (int i = 0; i < NPL; ++i) {
-            const uint64_t da = umma_desc(a0 + (uint32_t)i * aplane);
+            for (int i = 0; i < NPL; ++i) {
+              const uint64_t da = umma_desc(a0 + (uint32_t)i * aplane);
 #pragma unroll
-            for (int j = 0; j < NPL - i; ++j)  // accumulator i + j; its first product of an item is (0, j)
-              umma_i8(tm + (uint32_t)((i + j) * NBR), da, umma_desc(b0 + (uint32_t)j * S_PLANE), idesc,
-                      (c > 0 || i > 0) ? 1u : 0u);
+              for (int j = 0; j < NPL - i; ++j)  // accumulator i + j; its first product of an item is (0, j)
+                umma_i8(tm + (uint32_t)((i + j) * NBR), da, umma_desc(b0 + (uint32_t)j * S_PLANE), idesc,
+                        (c > 0 || i > 0) ? 1u : 0u);
+            }
+            umma_commit(&sm.g_empty[sg]);   // both arrive when the MMAs above have read their operands
+            umma_commit(&sm.s_empty[ss]);
+          } else {
+            // this stage's planes are in TMEM already (copied behind the previous stage's MMAs); the next stage's
+            // plane i is copied right after the last MMA that reads plane i (tcgen05 ops execute in issue order)
+            const bool last = c + 1 == pm.i8_nst;
+            const uint32_t ap1 = last ? aplane_next_item : aplane;  // 0: no further stage on this CTA
+            const uint32_t k1 = k + 1, sg1 = k1 % (uint32_t)ar.gst;
+            if (ap1) wait_wd(&sm.g_full[sg1], (k1 / (uint32_t)ar.gst) & 1u, 4, k1, true);
+            wait_wd(&sm.s_full[ss], (k / SST) & 1u, 5, k, true);
+            tc_fence_after();
+            const uint32_t a1 = smem_u32(sm.G + (size_t)sg1 * ar.gslot);
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+#pragma unroll
+              for (int j = 0; j < NPL - i; ++j)
+                umma_i8_ts(tm + (uint32_t)((i + j) * NBR), ta + 8 * i, umma_desc(b0 + (uint32_t)j * S_PLANE), idesc,
+                           (c > 0 || i > 0) ? 1u : 0u);
+              if (ap1) tmem_cp_plane(ta + 8 * i, umma_desc(a1 + (uint32_t)i * ap1));
+            }
+            if (ap1) umma_commit(&sm.g_empty[sg1]);  // the next stage's planes have left shared memory
+            umma_commit(&sm.s_empty[ss]);
           }
-          umma_commit(&sm.g_empty[sg]);   // both arrive when the MMAs above have read their operands
-          umma_commit(&sm.s_empty[ss]);
         }
         umma_commit(sm.acc_full);
       }
@@ -799,6 +847,8 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   const unsigned grid = (unsigned)(nwork < pk->num_sms ? nwork : pk->num_sms);
   // producer warps per CTA: a tuning knob while the kernel is being brought up (both variants compute the same bits)
   static const int npw = getenv("FASTFP_B200_I8_NPW") ? atoi(getenv("FASTFP_B200_I8_NPW")) : 8;
+  static const int ts = getenv("FASTFP_B200_I8_TS") ? atoi(getenv("FASTFP_B200_I8_TS")) : 0;
+  a.ts = ts;
   if (npw == 16) {
     if (nm) fp_sweep_i8_kernel<true, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
     else fp_sweep_i8_kernel<false, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
