@@ -160,6 +160,15 @@ static int upload_ragged(double** dst, const double* const* src, const fastfp_pa
   return 0;
 }
 
+// sum_i 1/N_i per pulsar in extended precision (the tensor sweep derives c N^-1 c from s N^-1 s with it)
+static void set_ninv_sums(fastfp_pack* pk, const double* const* Nvecs) {
+  for (int p = 0; p < pk->P; ++p) {
+    long double acc = 0.0L;
+    for (int i = 0; i < pk->meta[p].n; ++i) acc += 1.0L / (long double)Nvecs[p][i];
+    pk->meta[p].ninv_sum = (double)acc;
+  }
+}
+
 static void pack_free(fastfp_pack* pk) {
   if (!pk) return;
   DeviceGuard g(pk->device);
@@ -210,7 +219,10 @@ int fastfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
   if (!rc) rc = upload_ragged(&sg.d_T, Ts, pk, 1, st);
   if (!rc) rc = upload_ragged(&pk->d_L, sigmas, pk, 2, st);
   if (!rc) rc = launch_fp_precompute(pk, sg.d_toas, sg.d_res, sg.d_Nvec, sg.d_T, st);
-  if (!rc) rc = build_i8_planes(pk, st);  // digit planes for the tensor path when every pulsar fits its tile
+  if (!rc) {
+    set_ninv_sums(pk, Nvecs);
+    rc = build_i8_planes(pk, st);  // digit planes for the tensor path when every pulsar fits its tile
+  }
   if (rc) { pack_free(pk); return rc; }
   *out = pk;
   return FASTFP_OK;
@@ -269,6 +281,7 @@ int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* 
     if (e == cudaSuccess) e = cudaMemcpy(d_pf, pf.data(), pf.size() * 8, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = cuda_fail(e, "upload phiinv_fix");
   }
+  if (!rc) set_ninv_sums(pk, Nvecs);
   if (!rc) rc = nmfp_pack_finish(pk, sg.d_toas, sg.d_res, sg.d_Nvec, sg.d_T, d_TNT, d_pf, st);
   cudaFree(d_TNT);
   cudaFree(d_pf);

@@ -92,6 +92,7 @@ struct PulsarMeta {
   int64_t i8_off;      // tensor path: byte offset of this pulsar's digit-plane stages
   int32_t i8_rows;     // tensor path: rows stored per plane (basis rows + the w row, padded to 8)
   int32_t i8_nst;      // tensor path: stages of 32 TOAs
+  double ninv_sum;     // tensor path: sum_i 1/N_i (c N^-1 c = sum 1/N - s N^-1 s, so the producers form two sums, not three)
 };
 
 struct KernelCfg {  // run-time mirror of SweepCfg's parameters

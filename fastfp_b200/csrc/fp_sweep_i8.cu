@@ -19,11 +19,12 @@
 // One 768-thread CTA per SM, static round-robin over (pulsar, 32-frequency tile) work items, per stage of 32 TOAs:
 //   warp 0   lane 0: TMA -- one bulk copy of the stage's G planes (7 x rows x 32 bytes, already in the SWIZZLE_32B
 //            K-major operand layout) and one of its (t, 1/N) vectors, mbarrier rings
-//   warp 1   lane 0: 28 tcgen05.mma (M = 128: rows of G, N = 64: 32 frequencies x {sin, cos}, K = 32 TOAs) into the
-//            7 accumulators (7 x 64 = 448 of the 512 TMEM columns); tcgen05.commit frees the stage
+//   warps 1-3 lane 0: 28 tcgen05.mma (M = 128: rows of G, N = 64: 32 frequencies x {sin, cos}, K = 32 TOAs) into the
+//            7 accumulators (7 x 64 = 448 of the 512 TMEM columns), split by accumulator over three issuing threads;
+//            tcgen05.commit frees the stage
 //   warps 8-23 (producers, two groups alternating stages): sincos_cw of ((2 pi) f) t (fastfp.py:78-79 phase order),
-//            the digit split, 14 conflict-free 4-byte stores per thread into the B-operand planes, and the three
-//            fp64 sums s N^-1 s, s N^-1 c, c N^-1 c
+//            the digit split, 14 conflict-free 4-byte stores per thread into the B-operand planes, and the fp64
+//            sums s N^-1 s, s N^-1 c (c N^-1 c = sum 1/N - s N^-1 s)
 //   warps 4-7 (epilogue, one TMEM lane quarter each): tcgen05.ld, fp64 recombination, b = Y_s.Y_s, Y_s.Y_c, Y_c.Y_c
 //            over the basis rows, (s|r), (c|r) from the w row, pivoted 2x2 solve (jnp.linalg.solve at fastfp.py:90)
 // Shared memory is the bound: an M=128, N=64 MMA reads 6 KB of operands, 48 cycles at 128 B/clk (measured,
@@ -47,7 +48,7 @@ constexpr int S_PLANE = NBR * KT;      // 2048 bytes
 constexpr int S_STAGE = NPL * S_PLANE; // 14336 bytes
 constexpr int V_STAGE = KT * 16;       // (t, 1/N) per TOA
 constexpr int SST = 6, VST = 8;        // ring depths (even: a slot is always served by the same producer group)
-constexpr int NACC_COLS = NPL * NBR;   // 448 accumulator columns of tensor memory; the TS form keeps 56 more for the G planes
+constexpr int NISSUE = 3;               // MMA-issuing threads (control warps 1-3), each owning a set of accumulators
 // Warp layout: warps 0-3 control (TMA, MMA issue), 4-7 epilogue, 8.. producers. A stage is always produced by 8
 // warps (thread = one frequency x four TOAs); with NPW = 16 two groups of 8 alternate stages, with NPW = 8 one group
 // takes every stage and each producer thread gets twice the registers.
@@ -76,7 +77,6 @@ struct Args {
   int mvpad;
   int ntile, nwork;
   int gslot, gst;                // G ring: bytes per slot (7 x rows_max x 32), number of slots
-  int ts;                        // 1: the G planes are copied to tensor memory once per stage and the MMAs take A from there
 };
 
 // byte offset of (row r, K byte c) in a K-major tile with 32-byte rows, SWIZZLE_32B: 8-row groups of 256 bytes, the
@@ -185,18 +185,6 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// A from tensor memory (TS form): lane = row of G, 8 columns hold the row's 32 K-bytes (filled by tmem_cp_plane)
-__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// one digit plane (128 rows x 32 bytes, SWIZZLE_32B K-major in shared memory) -> 128 lanes x 8 columns of TMEM
-__device__ __forceinline__ void tmem_cp_plane(uint32_t tmem_a, uint64_t sdesc) {
-  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_a), "l"(sdesc) : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];\n" ::"l"((uint64_t)smem_u32(bar)) : "memory");
 }
@@ -213,16 +201,21 @@ __device__ __forceinline__ void reg_set_inc() { asm volatile("setmaxnreg.inc.syn
 template <int R>
 __device__ __forceinline__ void reg_set_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
-// x in [-1, 1] -> the 7 bytes of rint(x 2^54) + 0x80..80 with every byte XORed with 0x80: balanced signed digits,
-// most significant in byte 6. Two magic-constant roundings give hi = rint(x 2^26) and lo = rint((x - hi 2^-26) 2^54)
-// as integers in the low mantissa bits; Q = hi 2^28 + lo exactly.
+// x in [-1, 1] -> the 7 bytes of Q + 0x80..80, Q = x 2^54 rounded to nearest, every byte XORed with 0x80: balanced
+// signed digits, most significant in byte 6. INTEGER instructions only, on purpose: fp64 FMAs and tcgen05 MMAs exclude
+// each other on the SM (tools/probes/umma_fp64_overlap_probe.cu: DFMA throughput drops ~100x while MMAs are in flight),
+// so every producer operation that is not fp64 runs underneath the MMAs instead of next to them. The mantissa is
+// shifted into place by the exponent (|x| <= 1: Q = mant 2^(e - 1021), a right shift by 1021 - e with the half added
+// first; ties round away from zero, everything else exactly like rint).
 __device__ __forceinline__ uint2 digits7(double x) {
-  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  const double t1 = fma(x, 67108864.0, MAGIC);
-  const double rem = fma(-(t1 - MAGIC), 1.0 / 67108864.0, x);
-  const double t2 = fma(rem, 18014398509481984.0, MAGIC);
-  const long long hi = (long long)__double2loint(t1);
-  const long long U = hi * 268435456LL + (__double_as_longlong(t2) - 0x4338000000000000LL) + 0x0080808080808080LL;
+  const long long b = __double_as_longlong(x);
+  const int e = (int)((unsigned long long)b >> 52) & 0x7ff;
+  const unsigned long long mant = ((unsigned long long)b & 0x000fffffffffffffULL) | 0x0010000000000000ULL;
+  const int sh = 1021 - e;                      // >= -2 for |x| <= 1 (e <= 1023)
+  unsigned long long q = sh <= 0 ? mant << ((-sh) & 3) : (mant + (1ULL << ((sh - 1) & 63))) >> (sh & 63);
+  if (sh > 54) q = 0ULL;                        // |x| < 2^-55 (zero and denormals included)
+  const long long Q = b < 0 ? -(long long)q : (long long)q;
+  const long long U = Q + 0x0080808080808080LL;
   return make_uint2((uint32_t)U ^ 0x80808080u, (uint32_t)((unsigned long long)U >> 32) ^ 0x00808080u);
 }
 
@@ -282,10 +275,10 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
   Smem sm(smem_raw, ar);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < ar.gst; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], 1); }
+    for (int s = 0; s < ar.gst; ++s) { mbar_init(&sm.g_full[s], 1); mbar_init(&sm.g_empty[s], NISSUE); }
     for (int s = 0; s < VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 8); }
-    for (int s = 0; s < SST; ++s) { mbar_init(&sm.s_full[s], 8); mbar_init(&sm.s_empty[s], 1); }
-    mbar_init(sm.acc_full, 1);
+    for (int s = 0; s < SST; ++s) { mbar_init(&sm.s_full[s], 8); mbar_init(&sm.s_empty[s], NISSUE); }
+    mbar_init(sm.acc_full, NISSUE);
     mbar_init(sm.acc_empty, 4);
     for (int b = 0; b < 2; ++b) { mbar_init(&sm.sums_full[b], NPW); mbar_init(&sm.sums_empty[b], 1); }
     fence_barrier_init();
@@ -319,64 +312,39 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
           src += V_STAGE + gbytes;
         }
       }
-    } else if (wid == 1 && lane == 0) {
+    } else if (wid >= 1 && lane == 0) {
+      // Three MMA-issuing threads, one per remaining control warp (= one per SM sub-partition): a single issuer has to
+      // get ~12 instructions per MMA through a scheduler it shares with producer warps and was measured to be the
+      // critical path (it never waited: 2900 cycles per stage for 28 MMAs). Each issuer owns a set of accumulators
+      // (weights {6,1}, {5,2}, {4,3,0}: 9 + 9 + 10 products per stage), so no ordering between issuers is needed:
+      // every accumulator is written by one thread only, in that thread's program order.
+      const int q = wid - 1;
       // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NBR >> 3) << 17) | ((128u >> 4) << 24);
       uint32_t k = 0, it = 0;
-      const uint32_t ta = tm + (uint32_t)(NACC_COLS);   // TS form: 7 planes x 8 columns behind the accumulators
-      if (ar.ts && (int)blockIdx.x < ar.nwork) {        // planes of the very first stage
-        const PulsarMeta pm0 = ar.meta[ar.pidx[blockIdx.x / ar.ntile]];
-        wait_wd(&sm.g_full[0], 0u, 4, 0u, true);
-        tc_fence_after();
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) tmem_cp_plane(ta + 8 * i, umma_desc(smem_u32(sm.G) + (uint32_t)(i * pm0.i8_rows * KT)));
-        umma_commit(&sm.g_empty[0]);
-      }
       for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
         const PulsarMeta pm = ar.meta[ar.pidx[item / ar.ntile]];
         const uint32_t aplane = (uint32_t)(pm.i8_rows * KT);
-        const int nitem = item + (int)gridDim.x;
-        const uint32_t aplane_next_item = nitem < ar.nwork ? (uint32_t)(ar.meta[ar.pidx[nitem / ar.ntile]].i8_rows * KT) : 0u;
         if (it > 0) wait_wd(sm.acc_empty, (it - 1) & 1u, 3, it, true);  // the epilogue has drained the accumulators
         for (int c = 0; c < pm.i8_nst; ++c, ++k) {
           const uint32_t sg = k % (uint32_t)ar.gst, ss = k % SST;
-          const uint32_t b0 = smem_u32(sm.S + ss * S_STAGE);
-          if (!ar.ts) {
-            wait_wd(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k, true);
-            wait_wd(&sm.s_full[ss], (k / SST) & 1u, 5, k, true);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sm.G + (size_t)sg * ar.gslot);
+          wait_wd(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k, true);
+          wait_wd(&sm.s_full[ss], (k / SST) & 1u, 5, k, true);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sm.G + (size_t)sg * ar.gslot), b0 = smem_u32(sm.S + ss * S_STAGE);
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) {
-              const uint64_t da = umma_desc(a0 + (uint32_t)i * aplane);
+          for (int i = 0; i < NPL; ++i) {
+            const uint64_t da = umma_desc(a0 + (uint32_t)i * aplane);
 #pragma unroll
-              for (int j = 0; j < NPL - i; ++j)  // accumulator i + j; its first product of an item is (0, j)
+            for (int j = 0; j < NPL - i; ++j) {  // accumulator i + j; its first product of an item is (0, j)
+              constexpr int OWNER[NPL] = {2, 0, 1, 2, 2, 1, 0};
+              if (OWNER[i + j] == q)
                 umma_i8(tm + (uint32_t)((i + j) * NBR), da, umma_desc(b0 + (uint32_t)j * S_PLANE), idesc,
                         (c > 0 || i > 0) ? 1u : 0u);
             }
-            umma_commit(&sm.g_empty[sg]);   // both arrive when the MMAs above have read their operands
-            umma_commit(&sm.s_empty[ss]);
-          } else {
-            // this stage's planes are in TMEM already (copied behind the previous stage's MMAs); the next stage's
-            // plane i is copied right after the last MMA that reads plane i (tcgen05 ops execute in issue order)
-            const bool last = c + 1 == pm.i8_nst;
-            const uint32_t ap1 = last ? aplane_next_item : aplane;  // 0: no further stage on this CTA
-            const uint32_t k1 = k + 1, sg1 = k1 % (uint32_t)ar.gst;
-            if (ap1) wait_wd(&sm.g_full[sg1], (k1 / (uint32_t)ar.gst) & 1u, 4, k1, true);
-            wait_wd(&sm.s_full[ss], (k / SST) & 1u, 5, k, true);
-            tc_fence_after();
-            const uint32_t a1 = smem_u32(sm.G + (size_t)sg1 * ar.gslot);
-#pragma unroll
-            for (int i = 0; i < NPL; ++i) {
-#pragma unroll
-              for (int j = 0; j < NPL - i; ++j)
-                umma_i8_ts(tm + (uint32_t)((i + j) * NBR), ta + 8 * i, umma_desc(b0 + (uint32_t)j * S_PLANE), idesc,
-                           (c > 0 || i > 0) ? 1u : 0u);
-              if (ap1) tmem_cp_plane(ta + 8 * i, umma_desc(a1 + (uint32_t)i * ap1));
-            }
-            if (ap1) umma_commit(&sm.g_empty[sg1]);  // the next stage's planes have left shared memory
-            umma_commit(&sm.s_empty[ss]);
           }
+          umma_commit(&sm.g_empty[sg]);   // each issuer's commit arrives when ITS MMAs above have read their operands
+          umma_commit(&sm.s_empty[ss]);
         }
         umma_commit(sm.acc_full);
       }
@@ -496,10 +464,11 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
 #pragma unroll
           for (int k2 = 0; k2 < 3; ++k2) b[k2] += sm.part[((size_t)w2 * NF + f) * 3 + k2];
 #pragma unroll
-        for (int k2 = 0; k2 < 3; ++k2) {
+        for (int k2 = 0; k2 < 2; ++k2) {
           a[k2] = sm.redA[((buf * 2 + 0) * NF + f) * 3 + k2];
           if (NG == 2) a[k2] += sm.redA[((buf * 2 + 1) * NF + f) * 3 + k2];
         }
+        a[2] = pm.ninv_sum - a[0];  // c N^-1 c = sum 1/N - s N^-1 s (s^2 + c^2 = 1 to the last bit of the sincos values)
         const double N0 = sm.nval[2 * f], N1 = sm.nval[2 * f + 1];
         // M = [[ss, sc],[sc, cc]], N = [n0, n1]; LU with partial pivoting
         double m00 = a[0] - b[0], m01 = a[1] - b[1], m10 = m01, m11 = a[2] - b[2];
@@ -551,7 +520,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       const double fq = ar.freqs[f0 + f < ar.F ? f0 + f : f0];  // a short last tile repeats its first frequency
       const double omega = __dmul_rn(6.283185307179586, fq);     // (2*pi)*f, rounded once (fastfp.py:78)
       const bool fast = __all_sync(0xffffffffu, fabs(omega) * pm.tabs_max <= 0.999 * FFP_SINCOS_MAX);
-      double s3[3] = {0.0, 0.0, 0.0};
+      double s3[2] = {0.0, 0.0};  // s N^-1 s, s N^-1 c
       const int nst = pm.i8_nst;
       const int c0 = NG == 1 ? 0 : (int)((kbase ^ grp) & 1u);
       for (int c = c0; c < nst; c += NG) {
@@ -574,10 +543,9 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
           uint32_t slo[4], shi[4], clo[4], chi[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const double sn = sv4[e] * ninv[e], cn = cv4[e] * ninv[e];
+            const double sn = sv4[e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
             s3[0] = fma(sn, sv4[e], s3[0]);
             s3[1] = fma(sn, cv4[e], s3[1]);
-            s3[2] = fma(cn, cv4[e], s3[2]);
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -620,10 +588,9 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
             const double2 tn = vv[e];
             double sv1, cv1;
             sincos(__dmul_rn(omega, tn.x), &sv1, &cv1);
-            const double sn = sv1 * tn.y, cn = cv1 * tn.y;
+            const double sn = sv1 * tn.y;
             s3[0] = fma(sn, sv1, s3[0]);
             s3[1] = fma(sn, cv1, s3[1]);
-            s3[2] = fma(cn, cv1, s3[2]);
             const uint2 ds = digits7(sv1), dc = digits7(cv1);
             const unsigned long long us = ((unsigned long long)ds.y << 32) | ds.x, uc = ((unsigned long long)dc.y << 32) | dc.x;
 #pragma unroll
@@ -641,9 +608,9 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
         }
       }
       kbase += (uint32_t)nst;
-      // the three sums of frequency f: over the 8 lanes that share it (lane bits 2..4), then published per group
+      // the two sums of frequency f: over the 8 lanes that share it (lane bits 2..4), then published per group
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
+      for (int q = 0; q < 2; ++q) {
         double t = s3[q];
         t += __shfl_xor_sync(0xffffffffu, t, 4);
         t += __shfl_xor_sync(0xffffffffu, t, 8);
@@ -654,7 +621,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       if (it >= 2) wait_wd(&sm.sums_empty[buf], ((it >> 1) - 1) & 1u, 10, it, false);
       if (kg == 0) {
         double* o = sm.redA + ((buf * 2 + grp) * NF + f) * 3;
-        o[0] = s3[0]; o[1] = s3[1]; o[2] = s3[2];
+        o[0] = s3[0]; o[1] = s3[1];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.sums_full[buf]);
@@ -847,8 +814,6 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   const unsigned grid = (unsigned)(nwork < pk->num_sms ? nwork : pk->num_sms);
   // producer warps per CTA: a tuning knob while the kernel is being brought up (both variants compute the same bits)
   static const int npw = getenv("FASTFP_B200_I8_NPW") ? atoi(getenv("FASTFP_B200_I8_NPW")) : 8;
-  static const int ts = getenv("FASTFP_B200_I8_TS") ? atoi(getenv("FASTFP_B200_I8_TS")) : 0;
-  a.ts = ts;
   if (npw == 16) {
     if (nm) fp_sweep_i8_kernel<true, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
     else fp_sweep_i8_kernel<false, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);

@@ -288,7 +288,9 @@ __device__ __forceinline__ void consumer_loop(const SweepArgs& ar, SweepSmem<C>&
     };
     if (tid == 0)
       for (int c = 0; c < C::GST - 1 && c < nch; ++c) issue_G(c);  // chunks 0 .. GST-2 in flight
-    if (tid < C::KF) sm.fq[tid] = f0 + tid < ar.F ? ar.freqs[f0 + tid] : 1.0;
+    // a short last tile repeats its first frequency, so which sincos path a warp takes (and with it the last bits of
+    // a bin) never depends on how many bins were passed along with it
+    if (tid < C::KF) sm.fq[tid] = ar.freqs[f0 + tid < ar.F ? f0 + tid : f0];
     __syncthreads();  // B2
 
     double acc[NMBW][NNB][2];

@@ -19,8 +19,11 @@ def pytest_configure(config):
 def sweep_path(request, monkeypatch):
     """Run a plain-Fp GPU test on both sweep kernels: "auto" = the INT8 tensor-core kernel wherever the pack can take
     it (else the fp64 DMMA kernel), "fp64" = the DMMA kernel always. FastFp reads FASTFP_B200_PATH at construction."""
-    monkeypatch.setenv("FASTFP_B200_PATH", request.param)
-    return request.param
+    path = request.param
+    if path == "auto" and os.environ.get("FASTFP_B200_TEST_PREFER_I8"):
+        path = "prefer-i8"  # bring-up runs: exercise the tensor kernel before AUTO resolves to it
+    monkeypatch.setenv("FASTFP_B200_PATH", path)
+    return path
 
 
 class Psr:

@@ -29,7 +29,8 @@ def test_fe_matches_the_oracle_over_a_sky_grid():
     assert np.abs(got / want - 1).max() < 1e-5  # bins inside the red-noise band: ill-conditioned in the formula itself
     # batching forms
     # (NumPy's vectorised sin/cos of the sky-angle ARRAYS may differ from the scalar calls by an ulp, so the forms that
-    # change how the antenna patterns are evaluated are compared to 1e-13, the frequency batching bit for bit)
+    # change how the antenna patterns are evaluated are compared to 1e-13; the frequency batching is bit for bit: a bin
+    # does not depend on how many bins are swept with it)
     one = fe.calculate_Fe(float(freqs[3]), float(th[1]), float(ph[1]), *a)
     assert np.ndim(one) == 0 and abs(one / got[1, 3] - 1) < 1e-13
     np.testing.assert_allclose(fe.calculate_Fe(freqs, float(th[2]), float(ph[2]), *a), got[2], rtol=1e-13)

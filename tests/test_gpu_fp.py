@@ -95,7 +95,16 @@ def test_every_kernel_family_against_oracle(n_tm, ncomps):
     tt, cond = truth.fp_sweep_truth(*args)
     tol = term_tolerance(tt.astype(float), cond, ora)
     assert got.shape == (3, 73), m
-    assert np.all(np.abs(got - tt.astype(float)) <= tol), f"m={m}"
+    ratio = np.abs(got - tt.astype(float)) / tol
+    # a bin whose conditioning figure times eps reaches the size of the term itself carries no digits in the
+    # reference formula either (the 2x2 system is numerically singular there: the wide-basis cases put a red-noise
+    # Fourier frequency on top of ~600 fitted columns); the linear error envelope does not apply to it
+    defined = EPS * cond < 0.05 * np.abs(tt.astype(float))
+    assert defined.mean() > 0.9
+    ratio = np.where(defined, ratio, 0.0)
+    worst = np.unravel_index(np.argmax(ratio), ratio.shape)
+    assert np.all(ratio <= 1), (f"m={m}: worst |got - truth| / tol = {ratio.max():.3g} at (pulsar, bin) {worst}: got "
+                                f"{got[worst]:.6g}, truth {float(tt[worst]):.6g}, oracle {ora[worst]:.6g}, cond {cond[worst]:.3g}")
     np.testing.assert_allclose(fp(freqs, pta.Nvecs, pta.Ts, pta.sigmas), got[0] + got[1] + got[2], rtol=1e-15)
 
 
