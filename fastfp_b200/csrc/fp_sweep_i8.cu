@@ -201,20 +201,13 @@ __device__ __forceinline__ void reg_set_inc() { asm volatile("setmaxnreg.inc.syn
 template <int R>
 __device__ __forceinline__ void reg_set_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
-// x in [-1, 1] -> the 7 bytes of Q + 0x80..80, Q = x 2^54 rounded to nearest, every byte XORed with 0x80: balanced
-// signed digits, most significant in byte 6. INTEGER instructions only, on purpose: fp64 FMAs and tcgen05 MMAs exclude
-// each other on the SM (tools/probes/umma_fp64_overlap_probe.cu: DFMA throughput drops ~100x while MMAs are in flight),
-// so every producer operation that is not fp64 runs underneath the MMAs instead of next to them. The mantissa is
-// shifted into place by the exponent (|x| <= 1: Q = mant 2^(e - 1021), a right shift by 1021 - e with the half added
-// first; ties round away from zero, everything else exactly like rint).
+// x in [-1, 1] -> the 7 bytes of Q + 0x80..80, Q = rint(x 2^54), every byte XORed with 0x80: balanced signed digits,
+// most significant in byte 6. The scaling is an integer add on the exponent field (zero and subnormals land below
+// 2^-900 and round to 0; the fast path is entered for finite data only) and the rounding ONE conversion instruction
+// (F2I.S64.F64): conversions keep their rate while tcgen05 MMAs are in flight, fp64 multiplies and FMAs do not
+// (tools/probes/umma_fp64_overlap_probe.cu), and an all-integer extraction costs ~30 instructions per value.
 __device__ __forceinline__ uint2 digits7(double x) {
-  const long long b = __double_as_longlong(x);
-  const int e = (int)((unsigned long long)b >> 52) & 0x7ff;
-  const unsigned long long mant = ((unsigned long long)b & 0x000fffffffffffffULL) | 0x0010000000000000ULL;
-  const int sh = 1021 - e;                      // >= -2 for |x| <= 1 (e <= 1023)
-  unsigned long long q = sh <= 0 ? mant << ((-sh) & 3) : (mant + (1ULL << ((sh - 1) & 63))) >> (sh & 63);
-  if (sh > 54) q = 0ULL;                        // |x| < 2^-55 (zero and denormals included)
-  const long long Q = b < 0 ? -(long long)q : (long long)q;
+  const long long Q = __double2ll_rn(__hiloint2double(__double2hiint(x) + (54 << 20), __double2loint(x)));
   const long long U = Q + 0x0080808080808080LL;
   return make_uint2((uint32_t)U ^ 0x80808080u, (uint32_t)((unsigned long long)U >> 32) ^ 0x00808080u);
 }
@@ -227,13 +220,52 @@ __device__ __forceinline__ void wait_timeout(int tag, uint32_t k) {
          (int)blockIdx.x, (int)(threadIdx.x >> 5));
   __trap();
 }
-__device__ __forceinline__ void wait_wd(uint64_t* bar, uint32_t parity, int tag, uint32_t k, bool spin) {
+// mbarrier.try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or HINT_NS pass
+// (without the hint the time slice is a few tens of nanoseconds, and __nanosleep between polls was measured not to
+// lengthen it: the four epilogue warps alone executed a quarter of the kernel's instructions polling for their item).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      " selp.b32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// SLEEP_NS = 0: the waiter is on the critical path and polls with the default time slice; otherwise each poll may
+// suspend the warp for up to SLEEP_NS, so that waiting warps do not spend issue slots the producers need.
+template <int SLEEP_NS>
+__device__ __forceinline__ void wait_wd(uint64_t* bar, uint32_t parity, int tag, uint32_t k) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  constexpr uint32_t LIMIT = 1u << 28;   // >= 2 s at the shortest poll observed (~ 20 ns)
   uint32_t n = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (!spin) __nanosleep(64);
-    if ((++n & 1023u) == 0 && clock64() - t0 > 4000000000LL) wait_timeout(tag, k);
+  while (!(SLEEP_NS ? mbar_try_wait_hint(bar, parity, (uint32_t)SLEEP_NS) : mbar_try_wait(bar, parity))) {
+    if (++n > LIMIT) wait_timeout(tag, k);
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// The products of one 32-TOA stage that issuer Q owns: accumulator g = i + j collects plane i of G times plane j of
+// [s c]; the accumulators are dealt to the three issuers as {6, 1}, {5, 2}, {4, 3, 0} (9 + 9 + 10 products). Descriptors
+// differ in their 14-bit address field only, so each is one add on the low word of the stage's base descriptor.
+template <int Q>
+__device__ __forceinline__ void issue_stage(uint32_t tm, uint32_t da_lo, uint32_t db_lo, uint32_t aplane16,
+                                            uint32_t idesc, bool first_stage) {
+  constexpr uint32_t OWNER[NPL] = {2, 0, 1, 2, 2, 1, 0};
+  constexpr uint64_t HI = ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+#pragma unroll
+    for (int j = 0; j < NPL - i; ++j) {  // the first product into accumulator j of an item is (0, j)
+      if (OWNER[i + j] == (uint32_t)Q)
+        umma_i8(tm + (uint32_t)((i + j) * NBR), HI | (uint64_t)(da_lo + (uint32_t)i * aplane16),
+                HI | (uint64_t)(db_lo + (uint32_t)j * (S_PLANE >> 4)), idesc, (!first_stage || i > 0) ? 1u : 0u);
+    }
   }
 }
 
@@ -303,50 +335,52 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
         const unsigned char* src = ar.planes + pm.i8_off;
         for (int c = 0; c < pm.i8_nst; ++c, ++k) {
           const uint32_t sv = k % VST, sg = k % (uint32_t)ar.gst;
-          if (k >= VST) wait_wd(&sm.v_empty[sv], ((k / VST) - 1) & 1u, 1, k, false);
+          if (k >= VST) wait_wd<2000>(&sm.v_empty[sv], ((k / VST) - 1) & 1u, 1, k);
           mbar_expect_tx(&sm.v_full[sv], V_STAGE);
           tma_load_1d(sm.V + sv * V_STAGE, src, V_STAGE, &sm.v_full[sv]);
-          if (k >= (uint32_t)ar.gst) wait_wd(&sm.g_empty[sg], ((k / (uint32_t)ar.gst) - 1) & 1u, 2, k, false);
+          if (k >= (uint32_t)ar.gst) wait_wd<2000>(&sm.g_empty[sg], ((k / (uint32_t)ar.gst) - 1) & 1u, 2, k);
           mbar_expect_tx(&sm.g_full[sg], gbytes);
           tma_load_1d(sm.G + (size_t)sg * ar.gslot, src + V_STAGE, gbytes, &sm.g_full[sg]);
           src += V_STAGE + gbytes;
         }
       }
-    } else if (wid >= 1 && lane == 0) {
-      // Three MMA-issuing threads, one per remaining control warp (= one per SM sub-partition): a single issuer has to
-      // get ~12 instructions per MMA through a scheduler it shares with producer warps and was measured to be the
-      // critical path (it never waited: 2900 cycles per stage for 28 MMAs). Each issuer owns a set of accumulators
-      // (weights {6,1}, {5,2}, {4,3,0}: 9 + 9 + 10 products per stage), so no ordering between issuers is needed:
-      // every accumulator is written by one thread only, in that thread's program order.
-      const int q = wid - 1;
+    } else if (wid >= 1) {
+      // Three MMA-issuing warps, one per remaining control warp (= one per SM sub-partition). A single issuing thread
+      // was measured to be the critical path (it never waited: 2900 cycles per stage for 28 MMAs against 1344 of
+      // tensor time): next to producer warps it gets an issue slot only every few cycles. Each issuer owns a set of
+      // accumulators, so no ordering between issuers is needed: every accumulator is written by one thread only, in
+      // program order. The whole warp runs the loop with warp-uniform values (broadcast by shuffle, so that the
+      // compiler keeps descriptors in uniform registers instead of serialising lanes around every MMA) and one
+      // elected lane issues.
+      const bool leader = elect_one();
       // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NBR >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t tmu = __shfl_sync(0xffffffffu, tm, 0);
+      const uint32_t g0 = smem_u32(sm.G), s0 = smem_u32(sm.S);
       uint32_t k = 0, it = 0;
       for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
-        const PulsarMeta pm = ar.meta[ar.pidx[item / ar.ntile]];
-        const uint32_t aplane = (uint32_t)(pm.i8_rows * KT);
-        if (it > 0) wait_wd(sm.acc_empty, (it - 1) & 1u, 3, it, true);  // the epilogue has drained the accumulators
-        for (int c = 0; c < pm.i8_nst; ++c, ++k) {
+        const int pi = ar.pidx[item / ar.ntile];
+        const uint32_t aplane16 = __shfl_sync(0xffffffffu, (uint32_t)(ar.meta[pi].i8_rows * KT) >> 4, 0);
+        const int nst = __shfl_sync(0xffffffffu, ar.meta[pi].i8_nst, 0);
+        if (it > 0) wait_wd<0>(sm.acc_empty, (it - 1) & 1u, 3, it);  // the epilogue has drained the accumulators
+        for (int c = 0; c < nst; ++c, ++k) {
           const uint32_t sg = k % (uint32_t)ar.gst, ss = k % SST;
-          wait_wd(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k, true);
-          wait_wd(&sm.s_full[ss], (k / SST) & 1u, 5, k, true);
+          wait_wd<0>(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k);
+          wait_wd<0>(&sm.s_full[ss], (k / SST) & 1u, 5, k);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sm.G + (size_t)sg * ar.gslot), b0 = smem_u32(sm.S + ss * S_STAGE);
-#pragma unroll
-          for (int i = 0; i < NPL; ++i) {
-            const uint64_t da = umma_desc(a0 + (uint32_t)i * aplane);
-#pragma unroll
-            for (int j = 0; j < NPL - i; ++j) {  // accumulator i + j; its first product of an item is (0, j)
-              constexpr int OWNER[NPL] = {2, 0, 1, 2, 2, 1, 0};
-              if (OWNER[i + j] == q)
-                umma_i8(tm + (uint32_t)((i + j) * NBR), da, umma_desc(b0 + (uint32_t)j * S_PLANE), idesc,
-                        (c > 0 || i > 0) ? 1u : 0u);
-            }
+          const uint32_t da_lo = (((g0 + sg * (uint32_t)ar.gslot) >> 4) & 0x3fffu) | (1u << 16);
+          const uint32_t db_lo = (((s0 + ss * (uint32_t)S_STAGE) >> 4) & 0x3fffu) | (1u << 16);
+          if (leader) {
+            if (wid == 1) issue_stage<0>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
+            else if (wid == 2) issue_stage<1>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
+            else issue_stage<2>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
+            umma_commit(&sm.g_empty[sg]);  // each issuer's commit arrives when ITS MMAs above have read their operands
+            umma_commit(&sm.s_empty[ss]);
           }
-          umma_commit(&sm.g_empty[sg]);   // each issuer's commit arrives when ITS MMAs above have read their operands
-          umma_commit(&sm.s_empty[ss]);
+          __syncwarp();
         }
-        umma_commit(sm.acc_full);
+        if (leader) umma_commit(sm.acc_full);
+        __syncwarp();
       }
     }
   } else if (wid < 8) {
@@ -362,7 +396,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       const int64_t f0 = (int64_t)ft * NF;
       const double rs = ar.rowscale[(size_t)p * 128 + row];
       const bool has_rows = 32 * ew < pm.i8_rows;  // warp-uniform
-      wait_wd(sm.acc_full, it & 1u, 6, it, false);
+      wait_wd<100000>(sm.acc_full, it & 1u, 6, it);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < NF; c0 += 8) {
@@ -455,7 +489,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       asm volatile("bar.sync 1, 128;" ::: "memory");  // partial sums and the w-row values of the 4 warps are visible
       const uint32_t buf = it & 1u;
       if (ew == 0) {
-        wait_wd(&sm.sums_full[buf], (it >> 1) & 1u, 7, it, false);
+        wait_wd<2000>(&sm.sums_full[buf], (it >> 1) & 1u, 7, it);
         const int f = lane;
         const int64_t fidx = f0 + f;
         double b[3] = {0, 0, 0}, a[3];
@@ -526,8 +560,8 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       for (int c = c0; c < nst; c += NG) {
         const uint32_t k = kbase + (uint32_t)c;
         const uint32_t sv = k % VST, ss = k % SST;
-        wait_wd(&sm.v_full[sv], (k / VST) & 1u, 8, k, false);
-        if (k >= SST) wait_wd(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k, false);
+        wait_wd<2000>(&sm.v_full[sv], (k / VST) & 1u, 8, k);
+        if (k >= SST) wait_wd<2000>(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k);
         const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
         unsigned char* sb = sm.S + ss * S_STAGE + soff;
         if (fast) {
@@ -618,7 +652,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
         s3[q] = t;
       }
       const uint32_t buf = it & 1u;
-      if (it >= 2) wait_wd(&sm.sums_empty[buf], ((it >> 1) - 1) & 1u, 10, it, false);
+      if (it >= 2) wait_wd<2000>(&sm.sums_empty[buf], ((it >> 1) - 1) & 1u, 10, it);
       if (kg == 0) {
         double* o = sm.redA + ((buf * 2 + grp) * NF + f) * 3;
         o[0] = s3[0]; o[1] = s3[1];
@@ -666,7 +700,7 @@ __global__ void __launch_bounds__(64, 1) i8_peak_kernel(int iters, int* out) {
                   umma_desc(smem_u32(sB + j * B_PLANE)), idesc, (it > 0 || i > 0) ? 1u : 0u);
     }
     umma_commit(&bar);
-    wait_wd(&bar, 0u, 11, 0u, true);
+    wait_wd<0>(&bar, 0u, 11, 0u);
     if (out) out[blockIdx.x] = 1;
   }
   tc_fence_before();

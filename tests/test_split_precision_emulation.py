@@ -2,7 +2,7 @@
 
 The hoisted formulation the CUDA paths use (Sigma = L L^T, G = L^-1 T^T N^-1, w = C^-1 r) with Y = G [s c] computed
 exactly the way the INT8 kernel does it -- radix-256 balanced digit planes of G (per-row power-of-two scale, |g| < 1/4,
-Qg = rint(g 2^55)) and of sin/cos (Q = x 2^54 to nearest, the integer-only extraction of ``digits7`` reproduced bit for bit), planes stored in the SWIZZLE_32B K-major operand layout and read back through it, 28 exact integer plane products
+Qg = rint(g 2^55)) and of sin/cos (Q = rint(x 2^54), as ``digits7`` extracts them), planes stored in the SWIZZLE_32B K-major operand layout and read back through it, 28 exact integer plane products
 into 7 accumulators, Horner recombination in fp64, the w row supplying (s|r), (c|r) -- and everything else in fp64. It
 must meet the same envelope against the longdouble truth as the CUDA kernels do on the golden fixtures, including the
 ill-conditioned bins next to the red-noise Fourier frequencies; and the digit formats' invariants are checked directly.
@@ -25,20 +25,9 @@ def swz32(r, c):
 
 
 def digits7(x):
-    """fp_sweep_i8.cu::digits7 in NumPy (integer instructions only there: fp64 FMAs and tensor-core MMAs exclude each
-    other on the SM): x in [-1, 1] -> (7, ...) int8 balanced digits, most significant first. The mantissa shifted
-    into place by the exponent, half added before a right shift (ties away from zero)."""
-    x = np.asarray(x, dtype=np.float64)
-    b = x.view(np.int64)
-    e = ((b >> 52) & 0x7ff).astype(np.int64)
-    mant = ((b & 0x000fffffffffffff) | 0x0010000000000000).astype(np.uint64)
-    sh = 1021 - e
-    left = mant << np.where(sh <= 0, (-sh) & 3, 0).astype(np.uint64)
-    shr = np.where(sh > 0, sh & 63, 1).astype(np.uint64)
-    right = (mant + (np.uint64(1) << (shr - np.uint64(1)))) >> shr
-    q = np.where(sh <= 0, left, right).astype(np.int64)
-    q = np.where(sh > 54, 0, q)
-    Q = np.where(b < 0, -q, q)
+    """fp_sweep_i8.cu::digits7 in NumPy: x in [-1, 1] -> (7, ...) int8 balanced digits of Q = rint(x 2^54), most
+    significant first (the kernel scales by an exponent add and rounds with one F2I.S64.F64)."""
+    Q = np.rint(np.ldexp(np.asarray(x, dtype=np.float64), 54)).astype(np.int64)
     U = Q + BIAS
     return np.stack([(((U >> (8 * (6 - p))) & 0xff) ^ 0x80).astype(np.uint8).view(np.int8) for p in range(NPL)])
 
@@ -60,9 +49,7 @@ def test_digit_formats_are_exact_representations():
     Q = sum(d[p] * 256 ** (6 - p) for p in range(NPL))
     exact = [np.longdouble(v) * np.longdouble(2.0) ** 54 for v in x]
     want = np.array([int(np.rint(v)) for v in exact], dtype=np.int64)
-    tie = np.array([abs(v - np.floor(v)) == 0.5 for v in exact])
-    np.testing.assert_array_equal(Q[~tie], want[~tie])  # the seven digits ARE x 2^54 rounded to nearest ...
-    assert np.all(np.abs(Q[tie]) >= np.abs(want[tie]))  # ... (ties away from zero instead of to even)
+    np.testing.assert_array_equal(Q, want)  # the seven digits ARE x 2^54 rounded to nearest
     assert np.abs(x - Q * 2.0 ** -54).max() <= 2.0 ** -55  # i.e. sin/cos are quantised to within 2^-55
     G = rng.standard_normal((9, 300)) * 10.0 ** rng.uniform(-3, 3, (9, 1)) * 10.0 ** rng.uniform(-1, 1, (9, 300))
     planes, e = g_planes(G)
