@@ -546,7 +546,14 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
     const int kg = lane >> 2, fl = lane & 3;
     const int f = 4 * (pw & 7) + fl;                   // frequency inside the tile
     const int soff = swz32(f, 4 * kg);                 // word of TOAs 4kg..4kg+3 in row f (sin); cos row: + 1024
+    // Software pipeline around the one hardware fact that shapes this kernel: fp64 arithmetic and tcgen05 MMAs exclude
+    // each other on the SM (tools/probes/umma_fp64_overlap_probe.cu), everything else (conversions, integer, stores)
+    // runs underneath the MMAs. So a stage is announced (s_full) not when its planes are stored but after the fp64 part
+    // of the NEXT stage: the MMAs of stage k then run next to the integer part of stage k + 1 (digits, byte transpose,
+    // stores), and the fp64 part of stage k + 2 follows when the tensor pipe has drained -- instead of
+    // fp64 -> integer -> MMA strictly in sequence.
     uint32_t kbase = 0, it = 0;
+    int pend = -1;  // S slot whose planes are stored but not announced yet
     for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
       const int gp = item / ar.ntile, ft = item - gp * ar.ntile;
       const PulsarMeta pm = ar.meta[ar.pidx[gp]];
@@ -561,85 +568,77 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
         const uint32_t k = kbase + (uint32_t)c;
         const uint32_t sv = k % VST, ss = k % SST;
         wait_wd<2000>(&sm.v_full[sv], (k / VST) & 1u, 8, k);
-        if (k >= SST) wait_wd<2000>(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k);
         const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
-        unsigned char* sb = sm.S + ss * S_STAGE + soff;
+        // ---- fp64 part: four (TOA, frequency) pairs per thread
+        double ph[4], ninv[4], sv4[4], cv4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double2 tn = vv[e];                    // (t, 1/N)
+          ph[e] = __dmul_rn(omega, tn.x);              // ((2*pi)*f)*t, rounded once more
+          ninv[e] = tn.y;
+        }
         if (fast) {
-          // four (TOA, frequency) pairs in lockstep: phases inside the Cody-Waite range (checked once per item)
-          double ph[4], ninv[4], sv4[4], cv4[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const double2 tn = vv[e];                    // (t, 1/N)
-            ph[e] = __dmul_rn(omega, tn.x);              // ((2*pi)*f)*t, rounded once more
-            ninv[e] = tn.y;
-          }
-          sincos_cw_n<4>(ph, sv4, cv4);
-          uint32_t slo[4], shi[4], clo[4], chi[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const double sn = sv4[e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
-            s3[0] = fma(sn, sv4[e], s3[0]);
-            s3[1] = fma(sn, cv4[e], s3[1]);
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint2 ds = digits7(sv4[e]), dc = digits7(cv4[e]);
-            slo[e] = ds.x; shi[e] = ds.y; clo[e] = dc.x; chi[e] = dc.y;
-          }
-          // 4 x 7 byte transpose: word of plane p (most significant first) = byte (6 - p) of the four values
-          {
-            const uint32_t a = __byte_perm(slo[0], slo[1], 0x5140), b = __byte_perm(slo[0], slo[1], 0x7362);
-            const uint32_t c2 = __byte_perm(slo[2], slo[3], 0x5140), d = __byte_perm(slo[2], slo[3], 0x7362);
-            const uint32_t e2 = __byte_perm(shi[0], shi[1], 0x5140), f2 = __byte_perm(shi[0], shi[1], 0x7362);
-            const uint32_t g2 = __byte_perm(shi[2], shi[3], 0x5140), h2 = __byte_perm(shi[2], shi[3], 0x7362);
-            *reinterpret_cast<uint32_t*>(sb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);   // byte 0
-            *reinterpret_cast<uint32_t*>(sb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);   // byte 1
-            *reinterpret_cast<uint32_t*>(sb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);    // byte 2
-            *reinterpret_cast<uint32_t*>(sb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);    // byte 3
-            *reinterpret_cast<uint32_t*>(sb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);  // byte 4
-            *reinterpret_cast<uint32_t*>(sb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);  // byte 5
-            *reinterpret_cast<uint32_t*>(sb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);  // byte 6
-          }
-          {
-            unsigned char* cb = sb + NF * KT;  // cos rows 32..63
-            const uint32_t a = __byte_perm(clo[0], clo[1], 0x5140), b = __byte_perm(clo[0], clo[1], 0x7362);
-            const uint32_t c2 = __byte_perm(clo[2], clo[3], 0x5140), d = __byte_perm(clo[2], clo[3], 0x7362);
-            const uint32_t e2 = __byte_perm(chi[0], chi[1], 0x5140), f2 = __byte_perm(chi[0], chi[1], 0x7362);
-            const uint32_t g2 = __byte_perm(chi[2], chi[3], 0x5140), h2 = __byte_perm(chi[2], chi[3], 0x7362);
-            *reinterpret_cast<uint32_t*>(cb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);
-            *reinterpret_cast<uint32_t*>(cb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);
-            *reinterpret_cast<uint32_t*>(cb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);
-            *reinterpret_cast<uint32_t*>(cb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);
-            *reinterpret_cast<uint32_t*>(cb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);
-            *reinterpret_cast<uint32_t*>(cb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);
-            *reinterpret_cast<uint32_t*>(cb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);
-          }
+          sincos_cw_n<4>(ph, sv4, cv4);  // in lockstep: phases inside the Cody-Waite range (checked once per item)
         } else {
-          // cold: some phase of this item may exceed the Cody-Waite range (or is NaN/Inf): library sincos, one pair at
-          // a time, digits written byte by byte
-#pragma unroll 1
-          for (int e = 0; e < 4; ++e) {
-            const double2 tn = vv[e];
-            double sv1, cv1;
-            sincos(__dmul_rn(omega, tn.x), &sv1, &cv1);
-            const double sn = sv1 * tn.y;
-            s3[0] = fma(sn, sv1, s3[0]);
-            s3[1] = fma(sn, cv1, s3[1]);
-            const uint2 ds = digits7(sv1), dc = digits7(cv1);
-            const unsigned long long us = ((unsigned long long)ds.y << 32) | ds.x, uc = ((unsigned long long)dc.y << 32) | dc.x;
+          // cold: some phase of this item may exceed the Cody-Waite range (or is NaN/Inf): library sincos
 #pragma unroll
-            for (int p = 0; p < NPL; ++p) {
-              sb[p * S_PLANE + e] = (unsigned char)(us >> (8 * (6 - p)));
-              sb[p * S_PLANE + NF * KT + e] = (unsigned char)(uc >> (8 * (6 - p)));
-            }
+          for (int e = 0; e < 4; ++e) {  // unrolled: a dynamic index would put the arrays in local memory
+            double s1, c1;
+            sincos(ph[e], &s1, &c1);
+            sv4[e] = s1; cv4[e] = c1;
           }
         }
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double sn = sv4[e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
+          s3[0] = fma(sn, sv4[e], s3[0]);
+          s3[1] = fma(sn, cv4[e], s3[1]);
+        }
+        // ---- the previous stage's planes are complete: announce them now (see above)
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&sm.s_full[ss]);
           mbar_arrive(&sm.v_empty[sv]);
+          if (pend >= 0) mbar_arrive(&sm.s_full[pend]);
         }
+        // ---- integer part: digits, 4 x 7 byte transpose, stores
+        if (k >= SST) wait_wd<2000>(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k);
+        unsigned char* sb = sm.S + ss * S_STAGE + soff;
+        uint32_t slo[4], shi[4], clo[4], chi[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint2 ds = digits7(sv4[e]), dc = digits7(cv4[e]);
+          slo[e] = ds.x; shi[e] = ds.y; clo[e] = dc.x; chi[e] = dc.y;
+        }
+        // word of plane p (most significant first) = byte (6 - p) of the four values
+        {
+          const uint32_t a = __byte_perm(slo[0], slo[1], 0x5140), b = __byte_perm(slo[0], slo[1], 0x7362);
+          const uint32_t c2 = __byte_perm(slo[2], slo[3], 0x5140), d = __byte_perm(slo[2], slo[3], 0x7362);
+          const uint32_t e2 = __byte_perm(shi[0], shi[1], 0x5140), f2 = __byte_perm(shi[0], shi[1], 0x7362);
+          const uint32_t g2 = __byte_perm(shi[2], shi[3], 0x5140), h2 = __byte_perm(shi[2], shi[3], 0x7362);
+          *reinterpret_cast<uint32_t*>(sb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);   // byte 0
+          *reinterpret_cast<uint32_t*>(sb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);   // byte 1
+          *reinterpret_cast<uint32_t*>(sb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);    // byte 2
+          *reinterpret_cast<uint32_t*>(sb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);    // byte 3
+          *reinterpret_cast<uint32_t*>(sb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);  // byte 4
+          *reinterpret_cast<uint32_t*>(sb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);  // byte 5
+          *reinterpret_cast<uint32_t*>(sb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);  // byte 6
+        }
+        {
+          unsigned char* cb = sb + NF * KT;  // cos rows 32..63
+          const uint32_t a = __byte_perm(clo[0], clo[1], 0x5140), b = __byte_perm(clo[0], clo[1], 0x7362);
+          const uint32_t c2 = __byte_perm(clo[2], clo[3], 0x5140), d = __byte_perm(clo[2], clo[3], 0x7362);
+          const uint32_t e2 = __byte_perm(chi[0], chi[1], 0x5140), f2 = __byte_perm(chi[0], chi[1], 0x7362);
+          const uint32_t g2 = __byte_perm(chi[2], chi[3], 0x5140), h2 = __byte_perm(chi[2], chi[3], 0x7362);
+          *reinterpret_cast<uint32_t*>(cb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);
+          *reinterpret_cast<uint32_t*>(cb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);
+          *reinterpret_cast<uint32_t*>(cb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);
+          *reinterpret_cast<uint32_t*>(cb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);
+          *reinterpret_cast<uint32_t*>(cb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);
+          *reinterpret_cast<uint32_t*>(cb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);
+          *reinterpret_cast<uint32_t*>(cb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+        pend = (int)ss;
       }
       kbase += (uint32_t)nst;
       // the two sums of frequency f: over the 8 lanes that share it (lane bits 2..4), then published per group
@@ -660,6 +659,8 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.sums_full[buf]);
     }
+    __syncwarp();
+    if (lane == 0 && pend >= 0) mbar_arrive(&sm.s_full[pend]);  // the last stage of this CTA
   }
   tc_fence_before();
   __syncthreads();
