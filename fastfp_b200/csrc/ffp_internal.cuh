@@ -142,9 +142,9 @@ struct fastfp_pack {
   int i8_rows_max = 0;
   int64_t i8_bytes = 0;
   int path = 0;                   // FASTFP_PATH_AUTO / _FP64 / _I8 (fastfp_pack_set_path)
-  // AUTO resolves to the tensor path once that kernel has passed the GPU parity suite on hardware; until then the
-  // fp64 DMMA kernel stays the default and the tensor path is opt-in (path = FASTFP_PATH_I8)
-  static constexpr bool kAutoPrefersI8 = false;
+  // AUTO resolves to the tensor path wherever the pack can take it (it passed the GPU parity suite on hardware and is
+  // the faster kernel: profiles/README.md); FASTFP_PATH_FP64 forces the DMMA kernel
+  static constexpr bool kAutoPrefersI8 = true;
   bool use_i8() const { return i8_ok && (path == 2 || (path == 0 && kAutoPrefersI8)); }
   int64_t bytes = 0;
   int64_t mvar_total = 0;

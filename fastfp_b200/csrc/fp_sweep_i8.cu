@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "../../include/fastfp_b200.h"
 #include "ffp_internal.cuh"
@@ -77,7 +78,17 @@ struct Args {
   int mvpad;
   int ntile, nwork;
   int gslot, gst;                // G ring: bytes per slot (7 x rows_max x 32), number of slots
+  int excl;                      // 1: fp64 parts wait for the tensor pipe to drain (see the producers)
+#ifdef FFP_I8_TRACE
+  long long* trace;              // [TRACE_EV][TRACE_K] clock64 of CTA 0's first stages (tools/i8_trace.py)
+#endif
 };
+#ifdef FFP_I8_TRACE
+constexpr int TRACE_EV = 8, TRACE_K = 512;
+#define FFP_TRACE(ev, k) do { if (ar.trace && blockIdx.x == 0 && (k) < (uint32_t)TRACE_K) ar.trace[(ev) * TRACE_K + (k)] = clock64(); } while (0)
+#else
+#define FFP_TRACE(ev, k) do { } while (0)
+#endif
 
 // byte offset of (row r, K byte c) in a K-major tile with 32-byte rows, SWIZZLE_32B: 8-row groups of 256 bytes, the
 // 16-byte chunk index XORed with bit 2 of the row (validated by tools/probes/umma_i8_split_check.cu)
@@ -339,6 +350,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
           mbar_expect_tx(&sm.v_full[sv], V_STAGE);
           tma_load_1d(sm.V + sv * V_STAGE, src, V_STAGE, &sm.v_full[sv]);
           if (k >= (uint32_t)ar.gst) wait_wd<2000>(&sm.g_empty[sg], ((k / (uint32_t)ar.gst) - 1) & 1u, 2, k);
+          if (k >= (uint32_t)ar.gst) FFP_TRACE(0, k - (uint32_t)ar.gst);   // MMAs of stage k - gst have completed (seen by the TMA thread)
           mbar_expect_tx(&sm.g_full[sg], gbytes);
           tma_load_1d(sm.G + (size_t)sg * ar.gslot, src + V_STAGE, gbytes, &sm.g_full[sg]);
           src += V_STAGE + gbytes;
@@ -368,6 +380,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
           wait_wd<0>(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k);
           wait_wd<0>(&sm.s_full[ss], (k / SST) & 1u, 5, k);
           tc_fence_after();
+          if (wid == 1 && leader) FFP_TRACE(1, k);   // issuer 0 sees stage k complete
           const uint32_t da_lo = (((g0 + sg * (uint32_t)ar.gslot) >> 4) & 0x3fffu) | (1u << 16);
           const uint32_t db_lo = (((s0 + ss * (uint32_t)S_STAGE) >> 4) & 0x3fffu) | (1u << 16);
           if (leader) {
@@ -376,6 +389,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
             else issue_stage<2>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
             umma_commit(&sm.g_empty[sg]);  // each issuer's commit arrives when ITS MMAs above have read their operands
             umma_commit(&sm.s_empty[ss]);
+            if (wid == 1) FFP_TRACE(2, k);           // issuer 0 has issued its MMAs of stage k
           }
           __syncwarp();
         }
@@ -546,14 +560,52 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
     const int kg = lane >> 2, fl = lane & 3;
     const int f = 4 * (pw & 7) + fl;                   // frequency inside the tile
     const int soff = swz32(f, 4 * kg);                 // word of TOAs 4kg..4kg+3 in row f (sin); cos row: + 1024
-    // Software pipeline around the one hardware fact that shapes this kernel: fp64 arithmetic and tcgen05 MMAs exclude
-    // each other on the SM (tools/probes/umma_fp64_overlap_probe.cu), everything else (conversions, integer, stores)
-    // runs underneath the MMAs. So a stage is announced (s_full) not when its planes are stored but after the fp64 part
-    // of the NEXT stage: the MMAs of stage k then run next to the integer part of stage k + 1 (digits, byte transpose,
-    // stores), and the fp64 part of stage k + 2 follows when the tensor pipe has drained -- instead of
-    // fp64 -> integer -> MMA strictly in sequence.
+    // The schedule is built around one hardware fact: fp64 arithmetic and tcgen05 MMAs share a resource on the SM
+    // (tools/probes/umma_fp64_overlap_probe.cu: back-to-back MMAs starve DFMAs; tools/i8_trace.py: next to each other
+    // both run at ~80% of their combined rate, and a warp stalled on the fp64 pipe cannot issue its integer work
+    // either). Everything else (conversions, integer, stores) is free underneath the MMAs. So the two are kept apart:
+    //   fp64 part of stage k (A_k)  starts when the MMAs of stage k - NG - 1 have completed (tensor pipe idle),
+    //   stage k - NG is announced (s_full) after A_k,  its MMAs then run next to the integer part B_k (digits, byte
+    //   transpose, stores),  and A_{k+NG} waits for them.
+    auto store_planes = [&](const double (&sv4)[4], const double (&cv4)[4], unsigned char* sb) {
+      uint32_t slo[4], shi[4], clo[4], chi[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint2 ds = digits7(sv4[e]), dc = digits7(cv4[e]);
+        slo[e] = ds.x; shi[e] = ds.y; clo[e] = dc.x; chi[e] = dc.y;
+      }
+      // word of plane p (most significant first) = byte (6 - p) of the four values
+      {
+        const uint32_t a = __byte_perm(slo[0], slo[1], 0x5140), b = __byte_perm(slo[0], slo[1], 0x7362);
+        const uint32_t c2 = __byte_perm(slo[2], slo[3], 0x5140), d = __byte_perm(slo[2], slo[3], 0x7362);
+        const uint32_t e2 = __byte_perm(shi[0], shi[1], 0x5140), f2 = __byte_perm(shi[0], shi[1], 0x7362);
+        const uint32_t g2 = __byte_perm(shi[2], shi[3], 0x5140), h2 = __byte_perm(shi[2], shi[3], 0x7362);
+        *reinterpret_cast<uint32_t*>(sb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);   // byte 0
+        *reinterpret_cast<uint32_t*>(sb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);   // byte 1
+        *reinterpret_cast<uint32_t*>(sb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);    // byte 2
+        *reinterpret_cast<uint32_t*>(sb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);    // byte 3
+        *reinterpret_cast<uint32_t*>(sb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);  // byte 4
+        *reinterpret_cast<uint32_t*>(sb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);  // byte 5
+        *reinterpret_cast<uint32_t*>(sb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);  // byte 6
+      }
+      {
+        unsigned char* cb = sb + NF * KT;  // cos rows 32..63
+        const uint32_t a = __byte_perm(clo[0], clo[1], 0x5140), b = __byte_perm(clo[0], clo[1], 0x7362);
+        const uint32_t c2 = __byte_perm(clo[2], clo[3], 0x5140), d = __byte_perm(clo[2], clo[3], 0x7362);
+        const uint32_t e2 = __byte_perm(chi[0], chi[1], 0x5140), f2 = __byte_perm(chi[0], chi[1], 0x7362);
+        const uint32_t g2 = __byte_perm(chi[2], chi[3], 0x5140), h2 = __byte_perm(chi[2], chi[3], 0x7362);
+        *reinterpret_cast<uint32_t*>(cb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);
+        *reinterpret_cast<uint32_t*>(cb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);
+        *reinterpret_cast<uint32_t*>(cb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);
+        *reinterpret_cast<uint32_t*>(cb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);
+        *reinterpret_cast<uint32_t*>(cb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);
+        *reinterpret_cast<uint32_t*>(cb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);
+        *reinterpret_cast<uint32_t*>(cb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);
+      }
+    };
     uint32_t kbase = 0, it = 0;
     int pend = -1;  // S slot whose planes are stored but not announced yet
+    const bool EXCL = ar.excl != 0;
     for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
       const int gp = item / ar.ntile, ft = item - gp * ar.ntile;
       const PulsarMeta pm = ar.meta[ar.pidx[gp]];
@@ -568,8 +620,12 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
         const uint32_t k = kbase + (uint32_t)c;
         const uint32_t sv = k % VST, ss = k % SST;
         wait_wd<2000>(&sm.v_full[sv], (k / VST) & 1u, 8, k);
+        if (EXCL && k >= (uint32_t)(NG + 1)) {  // the tensor pipe has drained: MMAs complete in order
+          const uint32_t j = k - (uint32_t)(NG + 1);
+          wait_wd<2000>(&sm.s_empty[j % SST], (j / SST) & 1u, 12, k);
+        }
         const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
-        // ---- fp64 part: four (TOA, frequency) pairs per thread
+        if (pw == 0 && lane == 0) FFP_TRACE(3, k);   // fp64 part of stage k starts (inputs present)
         double ph[4], ninv[4], sv4[4], cv4[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -594,50 +650,16 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
           s3[0] = fma(sn, sv4[e], s3[0]);
           s3[1] = fma(sn, cv4[e], s3[1]);
         }
-        // ---- the previous stage's planes are complete: announce them now (see above)
         __syncwarp();
         if (lane == 0) {
+          if (pw == 0) FFP_TRACE(4, k);              // fp64 part of stage k done
           mbar_arrive(&sm.v_empty[sv]);
           if (pend >= 0) mbar_arrive(&sm.s_full[pend]);
         }
-        // ---- integer part: digits, 4 x 7 byte transpose, stores
         if (k >= SST) wait_wd<2000>(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k);
-        unsigned char* sb = sm.S + ss * S_STAGE + soff;
-        uint32_t slo[4], shi[4], clo[4], chi[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint2 ds = digits7(sv4[e]), dc = digits7(cv4[e]);
-          slo[e] = ds.x; shi[e] = ds.y; clo[e] = dc.x; chi[e] = dc.y;
-        }
-        // word of plane p (most significant first) = byte (6 - p) of the four values
-        {
-          const uint32_t a = __byte_perm(slo[0], slo[1], 0x5140), b = __byte_perm(slo[0], slo[1], 0x7362);
-          const uint32_t c2 = __byte_perm(slo[2], slo[3], 0x5140), d = __byte_perm(slo[2], slo[3], 0x7362);
-          const uint32_t e2 = __byte_perm(shi[0], shi[1], 0x5140), f2 = __byte_perm(shi[0], shi[1], 0x7362);
-          const uint32_t g2 = __byte_perm(shi[2], shi[3], 0x5140), h2 = __byte_perm(shi[2], shi[3], 0x7362);
-          *reinterpret_cast<uint32_t*>(sb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);   // byte 0
-          *reinterpret_cast<uint32_t*>(sb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);   // byte 1
-          *reinterpret_cast<uint32_t*>(sb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);    // byte 2
-          *reinterpret_cast<uint32_t*>(sb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);    // byte 3
-          *reinterpret_cast<uint32_t*>(sb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);  // byte 4
-          *reinterpret_cast<uint32_t*>(sb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);  // byte 5
-          *reinterpret_cast<uint32_t*>(sb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);  // byte 6
-        }
-        {
-          unsigned char* cb = sb + NF * KT;  // cos rows 32..63
-          const uint32_t a = __byte_perm(clo[0], clo[1], 0x5140), b = __byte_perm(clo[0], clo[1], 0x7362);
-          const uint32_t c2 = __byte_perm(clo[2], clo[3], 0x5140), d = __byte_perm(clo[2], clo[3], 0x7362);
-          const uint32_t e2 = __byte_perm(chi[0], chi[1], 0x5140), f2 = __byte_perm(chi[0], chi[1], 0x7362);
-          const uint32_t g2 = __byte_perm(chi[2], chi[3], 0x5140), h2 = __byte_perm(chi[2], chi[3], 0x7362);
-          *reinterpret_cast<uint32_t*>(cb + 6 * S_PLANE) = __byte_perm(a, c2, 0x5410);
-          *reinterpret_cast<uint32_t*>(cb + 5 * S_PLANE) = __byte_perm(a, c2, 0x7632);
-          *reinterpret_cast<uint32_t*>(cb + 4 * S_PLANE) = __byte_perm(b, d, 0x5410);
-          *reinterpret_cast<uint32_t*>(cb + 3 * S_PLANE) = __byte_perm(b, d, 0x7632);
-          *reinterpret_cast<uint32_t*>(cb + 2 * S_PLANE) = __byte_perm(e2, g2, 0x5410);
-          *reinterpret_cast<uint32_t*>(cb + 1 * S_PLANE) = __byte_perm(e2, g2, 0x7632);
-          *reinterpret_cast<uint32_t*>(cb + 0 * S_PLANE) = __byte_perm(f2, h2, 0x5410);
-        }
+        store_planes(sv4, cv4, sm.S + ss * S_STAGE + soff);
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+        if (pw == 0 && lane == 0) FFP_TRACE(5, k);   // planes of stage k stored
         pend = (int)ss;
       }
       kbase += (uint32_t)nst;
@@ -848,7 +870,18 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   }
   const unsigned grid = (unsigned)(nwork < pk->num_sms ? nwork : pk->num_sms);
   // producer warps per CTA: a tuning knob while the kernel is being brought up (both variants compute the same bits)
-  static const int npw = getenv("FASTFP_B200_I8_NPW") ? atoi(getenv("FASTFP_B200_I8_NPW")) : 8;
+#ifdef FFP_I8_TRACE
+  long long* d_trace = nullptr;
+  const char* trace_path = getenv("FASTFP_B200_I8_TRACE");
+  if (trace_path) {
+    FFP_CUDA(cudaMalloc(&d_trace, sizeof(long long) * TRACE_EV * TRACE_K));
+    FFP_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * TRACE_EV * TRACE_K, st));
+  }
+  a.trace = d_trace;
+#endif
+  static const int excl = getenv("FASTFP_B200_I8_EXCL") ? atoi(getenv("FASTFP_B200_I8_EXCL")) : 0;
+  a.excl = excl;
+  static const int npw = getenv("FASTFP_B200_I8_NPW") ? atoi(getenv("FASTFP_B200_I8_NPW")) : 16;
   if (npw == 16) {
     if (nm) fp_sweep_i8_kernel<true, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
     else fp_sweep_i8_kernel<false, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
@@ -858,6 +891,21 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   }
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
+#ifdef FFP_I8_TRACE
+  if (d_trace) {  // diagnostic build only: synchronous dump of CTA 0's event clocks
+    std::vector<long long> h((size_t)TRACE_EV * TRACE_K);
+    FFP_CUDA(cudaStreamSynchronize(st));
+    FFP_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    FFP_CUDA(cudaFree(d_trace));
+    if (FILE* fh = fopen(trace_path, "w")) {
+      for (int k = 0; k < TRACE_K; ++k) {
+        for (int e = 0; e < TRACE_EV; ++e) fprintf(fh, "%lld ", h[(size_t)e * TRACE_K + k]);
+        fprintf(fh, "\n");
+      }
+      fclose(fh);
+    }
+  }
+#endif
   return 0;
 }
 
