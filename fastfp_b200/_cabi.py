@@ -65,6 +65,7 @@ SYMBOLS = {
     "fastfp_pack_path": (C.c_int, [C.c_void_p]),
     "fastfp_pack_factor_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "fastfp_hash64": (C.c_uint64, [C.c_void_p, C.c_int64, C.c_uint64]),
+    "fastfp_hash64_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "fastfp_kernel_launches": (C.c_int64, []),
     "fastfp_xcy": (
         C.c_int,
@@ -174,6 +175,19 @@ def _check_lists(toas, residuals, Nvecs, Ts, mats, what):
 def hash64(a: np.ndarray, seed: int = 0) -> int:
     """64-bit hash of every byte of a C-contiguous host array (``fastfp_hash64``)."""
     return int(load().fastfp_hash64(C.c_void_p(a.ctypes.data), a.nbytes, C.c_uint64(seed & (2**64 - 1))))
+
+
+def hash64_many(arrays, seeds) -> list:
+    """``hash64`` of each C-contiguous host array in one library call (one thread pool over all of them)."""
+    n = len(arrays)
+    if n == 0:
+        return []
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    sizes = (C.c_int64 * n)(*[a.nbytes for a in arrays])
+    sd = (C.c_uint64 * n)(*[s & (2**64 - 1) for s in seeds])
+    out = (C.c_uint64 * n)()
+    check(load().fastfp_hash64_many(ptrs, sizes, n, sd, out))
+    return list(out)
 
 
 class Pack:

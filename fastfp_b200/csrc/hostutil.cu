@@ -5,6 +5,7 @@
 // (Nvecs, Ts, sigmas/TNTs) lists on each call: the device pack is a cache of those arrays, and the
 // reference is a pure function of its arguments (fastfp/fastfp.py:52), so an in-place edit of any entry
 // must rebuild the pack. (Round 1 sampled 16 points per array; an edit between the samples went unseen.)
+#include <atomic>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -35,31 +36,65 @@ uint64_t hash_block(const unsigned char* p, size_t n, uint64_t seed) {
   return mix(h);
 }
 
-}  // namespace
+constexpr size_t BLK = (size_t)4 << 20;  // fixed blocks: a hash value does not depend on the thread count
 
-extern "C" uint64_t fastfp_hash64(const void* data, int64_t nbytes, uint64_t seed) {
-  if (!data || nbytes <= 0) return mix(seed ^ 0x51ed270b7a1c2d4fULL);
-  const unsigned char* p = static_cast<const unsigned char*>(data);
-  const size_t n = (size_t)nbytes, BLK = (size_t)4 << 20;  // fixed blocks: the value does not depend on the thread count
-  const size_t nblk = (n + BLK - 1) / BLK;
-  std::vector<uint64_t> part(nblk);
-  auto work = [&](size_t b0, size_t b1) {
-    for (size_t b = b0; b < b1; ++b) {
-      const size_t lo = b * BLK, len = lo + BLK <= n ? BLK : n - lo;
-      part[b] = hash_block(p + lo, len, seed + b);
-    }
-  };
-  unsigned nt = std::thread::hardware_concurrency();
-  nt = nt > 16 ? 16 : (nt < 1 ? 1 : nt);
-  if (nblk < 4 || nt == 1) {
-    work(0, nblk);
-  } else {
-    if (nt > nblk) nt = (unsigned)nblk;
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, nblk * t / nt, nblk * (t + 1) / nt);
-    for (auto& t : th) t.join();
-  }
+inline uint64_t combine(const uint64_t* part, size_t nblk, size_t n, uint64_t seed) {
   uint64_t h = seed ^ (uint64_t)n;
   for (size_t b = 0; b < nblk; ++b) h = mix(h ^ part[b]) + 0x9E3779B97F4A7C15ULL * (b + 1);
   return mix(h);
+}
+
+unsigned pool_size(size_t nitems) {
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt > 32 ? 32 : (nt < 1 ? 1 : nt);
+  return nt > nitems ? (unsigned)nitems : nt;
+}
+}  // namespace
+
+// n buffers in one call: the (buffer, 4 MiB block) pieces of ALL of them are dealt to one set of threads, so a list of
+// many medium-sized arrays (one T matrix per pulsar: 3-6 MB each) hashes at memory bandwidth too -- per-array calls ran
+// those single-threaded, ~18 ms per C2-sized call, which bounded the step time of the short workloads from the host side.
+// out[i] equals fastfp_hash64(ptrs[i], nbytes[i], seeds[i]).
+extern "C" int fastfp_hash64_many(const void* const* ptrs, const int64_t* nbytes, int32_t n, const uint64_t* seeds,
+                                  uint64_t* out) {
+  if (n < 0 || (n > 0 && (!ptrs || !nbytes || !seeds || !out))) return FASTFP_ERR_INVALID;
+  std::vector<size_t> first((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    if (nbytes[i] < 0 || (nbytes[i] > 0 && !ptrs[i])) return FASTFP_ERR_INVALID;
+    first[(size_t)i + 1] = first[i] + ((size_t)nbytes[i] + BLK - 1) / BLK;
+  }
+  const size_t nitems = first[(size_t)n];
+  std::vector<uint64_t> part(nitems);
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    int i = 0;
+    for (;;) {
+      const size_t it = next.fetch_add(1, std::memory_order_relaxed);
+      if (it >= nitems) return;
+      while (first[(size_t)i + 1] <= it) ++i;  // items are handed out in increasing order
+      const size_t b = it - first[i], nb = (size_t)nbytes[i], lo = b * BLK;
+      part[it] = hash_block(static_cast<const unsigned char*>(ptrs[i]) + lo, lo + BLK <= nb ? BLK : nb - lo, seeds[i] + b);
+    }
+  };
+  const unsigned nt = pool_size(nitems);
+  if (nt <= 1 || nitems < 4) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t + 1 < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  for (int i = 0; i < n; ++i)
+    out[i] = nbytes[i] > 0 ? combine(part.data() + first[i], first[(size_t)i + 1] - first[i], (size_t)nbytes[i], seeds[i])
+                           : mix(seeds[i] ^ 0x51ed270b7a1c2d4fULL);
+  return 0;
+}
+
+extern "C" uint64_t fastfp_hash64(const void* data, int64_t nbytes, uint64_t seed) {
+  if (!data || nbytes <= 0) return mix(seed ^ 0x51ed270b7a1c2d4fULL);
+  uint64_t out = 0;
+  const void* p = data;
+  fastfp_hash64_many(&p, &nbytes, 1, &seed, &out);
+  return out;
 }

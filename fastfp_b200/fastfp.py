@@ -27,7 +27,7 @@ def _fingerprint(lists) -> tuple:
     (``fastfp_hash64``: memory-bandwidth class, threaded for large arrays). The reference is a pure function
     of these arguments (``fastfp/fastfp.py:52``), so the cached device pack must be rebuilt whenever any
     entry changes -- including in-place edits, which an address- or sample-based key cannot see."""
-    key = []
+    key, arrays, seeds, slots = [], [], [], []
     for lst in lists:
         key.append(len(lst))
         for a in lst:
@@ -35,7 +35,12 @@ def _fingerprint(lists) -> tuple:
                 if hasattr(a, "_nvec") else [a]
             for x in parts:
                 x = np.ascontiguousarray(x)
-                key.append((x.shape, x.dtype.str, _cabi.hash64(x, seed=len(key))))
+                slots.append(len(key))
+                seeds.append(len(key))
+                arrays.append(x)
+                key.append((x.shape, x.dtype.str))
+    for slot, h in zip(slots, _cabi.hash64_many(arrays, seeds)):  # one call: all arrays share the hashing threads
+        key[slot] = key[slot] + (h,)
     return tuple(key)
 
 

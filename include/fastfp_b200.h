@@ -168,6 +168,9 @@ int fastfp_pack_factor_info(const fastfp_pack_t* pack, int32_t* info);
 /* 64-bit content hash of a host buffer (multi-threaded for large buffers; deterministic): what the Python
  * mirror uses to key its pack cache on every byte of the caller's arrays. */
 uint64_t fastfp_hash64(const void* data, int64_t nbytes, uint64_t seed);
+/* the same for n buffers in one call (out[i] == fastfp_hash64(ptrs[i], nbytes[i], seeds[i])): the pieces of all
+ * buffers share one set of threads, so a list of many medium-sized arrays hashes at memory bandwidth. */
+int fastfp_hash64_many(const void* const* ptrs, const int64_t* nbytes, int32_t n, const uint64_t* seeds, uint64_t* out);
 int64_t fastfp_kernel_launches(void); /* kernels launched by this library so far (process-wide) */
 /* measurement aid: with enable != 0 every later fastfp_nmfp_sweep on this pack brackets its three
  * stages with CUDA events on the caller's stream and synchronises at the end; fastfp_nmfp_stage_ms

@@ -180,3 +180,7 @@ def test_pack_cache_key_sees_every_byte():
     swapped = big.copy()
     swapped[[5, 2_000_000]] = swapped[[2_000_000, 5]]
     assert _cabi.hash64(swapped) != h
+    # many buffers in one call (what _fingerprint uses): identical to the per-buffer values, empty buffers included
+    arrs = [big, big[:1000].copy(), np.zeros(0), rng.standard_normal((700, 9))]
+    assert _cabi.hash64_many(arrs, [0, 5, 6, 7]) == [_cabi.hash64(a, seed=s) for a, s in zip(arrs, [0, 5, 6, 7])]
+    assert _cabi.hash64_many([], []) == []
