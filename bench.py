@@ -96,8 +96,8 @@ def measured_traffic(workload):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 d = json.load(f)[workload]
-            return float(d["dram_bytes_per_launch"]), f"profiles/{name} (ncu --set full, per launch, one GPU's shard: " \
-                                                      f"{d.get('shard', 'see file')})"
+            return float(d["dram_bytes_per_launch"]), f"profiles/{name}: {d.get('kernel', 'dominant kernel')}, per launch, " \
+                                                      f"{d.get('shard', 'one GPU shard')}"
         except (OSError, KeyError, ValueError):
             continue
     return None, None
