@@ -310,8 +310,9 @@ struct Smem {
 constexpr size_t SMEM_FIXED = (size_t)SST * S_STAGE + VST * V_STAGE + (2 * 2 * NF * 3 + 4 * NF * 3 + NF * 2) * 8 +
                               (8 + 8 + 2 * VST + 2 * SST + 2 + 4) * 8 + 16;
 
-template <bool NMFP, int NPW>
+template <bool NMFP, int NPW, int NB>
 __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(const Args ar) {
+  static_assert(NB == 1 || NPW == 8, "batches of several stages: one producer group (registers)");
   using R = Roles<NPW>;
   constexpr int NG = R::NG;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -339,21 +340,25 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
     // ================= control warpgroup: TMA (warp 0) and MMA issue (warp 1) =================
     reg_set_dec<R::REGS_CTRL>();
     if (wid == 0 && lane == 0) {
-      uint32_t k = 0;
+      // ring positions and phase parities are carried incrementally (a division by the runtime ring depth per stage
+      // costs ~25 dependent instructions on a thread that competes with 16 producer warps for issue slots)
+      uint32_t k = 0, sv = 0, vpar = 0, sg = 0, gpar = 0;
+      unsigned char* gdst = sm.G;
       for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x) {
         const PulsarMeta pm = ar.meta[ar.pidx[item / ar.ntile]];
         const uint32_t gbytes = (uint32_t)(NPL * pm.i8_rows * KT);
         const unsigned char* src = ar.planes + pm.i8_off;
         for (int c = 0; c < pm.i8_nst; ++c, ++k) {
-          const uint32_t sv = k % VST, sg = k % (uint32_t)ar.gst;
-          if (k >= VST) wait_wd<2000>(&sm.v_empty[sv], ((k / VST) - 1) & 1u, 1, k);
+          if (k >= VST) wait_wd<2000>(&sm.v_empty[sv], vpar ^ 1u, 1, k);
           mbar_expect_tx(&sm.v_full[sv], V_STAGE);
           tma_load_1d(sm.V + sv * V_STAGE, src, V_STAGE, &sm.v_full[sv]);
-          if (k >= (uint32_t)ar.gst) wait_wd<2000>(&sm.g_empty[sg], ((k / (uint32_t)ar.gst) - 1) & 1u, 2, k);
+          if (k >= (uint32_t)ar.gst) wait_wd<2000>(&sm.g_empty[sg], gpar ^ 1u, 2, k);
           if (k >= (uint32_t)ar.gst) FFP_TRACE(0, k - (uint32_t)ar.gst);   // MMAs of stage k - gst have completed (seen by the TMA thread)
           mbar_expect_tx(&sm.g_full[sg], gbytes);
-          tma_load_1d(sm.G + (size_t)sg * ar.gslot, src + V_STAGE, gbytes, &sm.g_full[sg]);
+          tma_load_1d(gdst, src + V_STAGE, gbytes, &sm.g_full[sg]);
           src += V_STAGE + gbytes;
+          if (++sv == VST) { sv = 0; vpar ^= 1u; }
+          if (++sg == (uint32_t)ar.gst) { sg = 0; gpar ^= 1u; gdst = sm.G; } else gdst += ar.gslot;
         }
       }
     } else if (wid >= 1) {
@@ -370,19 +375,19 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       const uint32_t tmu = __shfl_sync(0xffffffffu, tm, 0);
       const uint32_t g0 = smem_u32(sm.G), s0 = smem_u32(sm.S);
       uint32_t k = 0, it = 0;
+      uint32_t sg = 0, gpar = 0, ss = 0, spar = 0, ga = g0, sa = s0;  // ring positions, parities, slot addresses
       for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
         const int pi = ar.pidx[item / ar.ntile];
         const uint32_t aplane16 = __shfl_sync(0xffffffffu, (uint32_t)(ar.meta[pi].i8_rows * KT) >> 4, 0);
         const int nst = __shfl_sync(0xffffffffu, ar.meta[pi].i8_nst, 0);
         if (it > 0) wait_wd<0>(sm.acc_empty, (it - 1) & 1u, 3, it);  // the epilogue has drained the accumulators
         for (int c = 0; c < nst; ++c, ++k) {
-          const uint32_t sg = k % (uint32_t)ar.gst, ss = k % SST;
-          wait_wd<0>(&sm.g_full[sg], (k / (uint32_t)ar.gst) & 1u, 4, k);
-          wait_wd<0>(&sm.s_full[ss], (k / SST) & 1u, 5, k);
+          wait_wd<0>(&sm.g_full[sg], gpar, 4, k);
+          wait_wd<0>(&sm.s_full[ss], spar, 5, k);
           tc_fence_after();
           if (wid == 1 && leader) FFP_TRACE(1, k);   // issuer 0 sees stage k complete
-          const uint32_t da_lo = (((g0 + sg * (uint32_t)ar.gslot) >> 4) & 0x3fffu) | (1u << 16);
-          const uint32_t db_lo = (((s0 + ss * (uint32_t)S_STAGE) >> 4) & 0x3fffu) | (1u << 16);
+          const uint32_t da_lo = ((ga >> 4) & 0x3fffu) | (1u << 16);
+          const uint32_t db_lo = ((sa >> 4) & 0x3fffu) | (1u << 16);
           if (leader) {
             if (wid == 1) issue_stage<0>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
             else if (wid == 2) issue_stage<1>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
@@ -392,6 +397,8 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
             if (wid == 1) FFP_TRACE(2, k);           // issuer 0 has issued its MMAs of stage k
           }
           __syncwarp();
+          if (++sg == (uint32_t)ar.gst) { sg = 0; gpar ^= 1u; ga = g0; } else ga += (uint32_t)ar.gslot;
+          if (++ss == SST) { ss = 0; spar ^= 1u; sa = s0; } else sa += S_STAGE;
         }
         if (leader) umma_commit(sm.acc_full);
         __syncwarp();
@@ -604,7 +611,9 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       }
     };
     uint32_t kbase = 0, it = 0;
-    int pend = -1;  // S slot whose planes are stored but not announced yet
+    // stages whose planes are stored but not announced yet: pend_n consecutive stages of this group from pend_k on
+    uint32_t pend_k = 0;
+    int pend_n = 0;
     const bool EXCL = ar.excl != 0;
     for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
       const int gp = item / ar.ntile, ft = item - gp * ar.ntile;
@@ -616,51 +625,69 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       double s3[2] = {0.0, 0.0};  // s N^-1 s, s N^-1 c
       const int nst = pm.i8_nst;
       const int c0 = NG == 1 ? 0 : (int)((kbase ^ grp) & 1u);
-      for (int c = c0; c < nst; c += NG) {
-        const uint32_t k = kbase + (uint32_t)c;
-        const uint32_t sv = k % VST, ss = k % SST;
-        wait_wd<2000>(&sm.v_full[sv], (k / VST) & 1u, 8, k);
-        if (EXCL && k >= (uint32_t)(NG + 1)) {  // the tensor pipe has drained: MMAs complete in order
-          const uint32_t j = k - (uint32_t)(NG + 1);
-          wait_wd<2000>(&sm.s_empty[j % SST], (j / SST) & 1u, 12, k);
-        }
-        const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
-        if (pw == 0 && lane == 0) FFP_TRACE(3, k);   // fp64 part of stage k starts (inputs present)
-        double ph[4], ninv[4], sv4[4], cv4[4];
+      // NB stages per batch (NB > 1 with one producer group only): the fp64 parts of the batch back to back, then the
+      // announcement of the previous batch, then the integer parts -- every switch between fp64 work and MMAs costs a
+      // tensor-pipe fill and the fp64 part's latency-bound tail, a batch pays them once
+      for (int c = c0; c < nst; c += NG * NB) {
+        const uint32_t k0 = kbase + (uint32_t)c;
+        const int nb = NB == 1 ? 1 : min(NB, nst - c);
+        double svv[NB][4], cvv[NB][4];
+        if (pw == 0 && lane == 0) FFP_TRACE(3, k0);   // fp64 part of stage k0 starts
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double2 tn = vv[e];                    // (t, 1/N)
-          ph[e] = __dmul_rn(omega, tn.x);              // ((2*pi)*f)*t, rounded once more
-          ninv[e] = tn.y;
-        }
-        if (fast) {
-          sincos_cw_n<4>(ph, sv4, cv4);  // in lockstep: phases inside the Cody-Waite range (checked once per item)
-        } else {
-          // cold: some phase of this item may exceed the Cody-Waite range (or is NaN/Inf): library sincos
+        for (int h = 0; h < NB; ++h) {
+          if (h < nb) {
+            const uint32_t k = k0 + (uint32_t)h;
+            const uint32_t sv = k % VST;
+            wait_wd<2000>(&sm.v_full[sv], (k / VST) & 1u, 8, k);
+            if (EXCL && h == 0 && k >= (uint32_t)(NG + 1)) {  // the tensor pipe has drained: MMAs complete in order
+              const uint32_t j = k - (uint32_t)(NG + 1);
+              wait_wd<2000>(&sm.s_empty[j % SST], (j / SST) & 1u, 12, k);
+            }
+            const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
+            double ph[4], ninv[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {  // unrolled: a dynamic index would put the arrays in local memory
-            double s1, c1;
-            sincos(ph[e], &s1, &c1);
-            sv4[e] = s1; cv4[e] = c1;
+            for (int e = 0; e < 4; ++e) {
+              const double2 tn = vv[e];                    // (t, 1/N)
+              ph[e] = __dmul_rn(omega, tn.x);              // ((2*pi)*f)*t, rounded once more
+              ninv[e] = tn.y;
+            }
+            if (fast) {
+              sincos_cw_n<4>(ph, svv[h], cvv[h]);  // in lockstep: phases inside the Cody-Waite range (checked per item)
+            } else {
+              // cold: some phase of this item may exceed the Cody-Waite range (or is NaN/Inf): library sincos
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {  // unrolled: a dynamic index would put the arrays in local memory
+                double s1, c1;
+                sincos(ph[e], &s1, &c1);
+                svv[h][e] = s1; cvv[h][e] = c1;
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double sn = svv[h][e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
+              s3[0] = fma(sn, svv[h][e], s3[0]);
+              s3[1] = fma(sn, cvv[h][e], s3[1]);
+            }
           }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double sn = sv4[e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
-          s3[0] = fma(sn, sv4[e], s3[0]);
-          s3[1] = fma(sn, cv4[e], s3[1]);
         }
         __syncwarp();
         if (lane == 0) {
-          if (pw == 0) FFP_TRACE(4, k);              // fp64 part of stage k done
-          mbar_arrive(&sm.v_empty[sv]);
-          if (pend >= 0) mbar_arrive(&sm.s_full[pend]);
+          if (pw == 0) FFP_TRACE(4, k0);              // fp64 parts of the batch done
+          for (int h = 0; h < nb; ++h) mbar_arrive(&sm.v_empty[(k0 + (uint32_t)h) % VST]);
+          for (int h = 0; h < pend_n; ++h) mbar_arrive(&sm.s_full[(pend_k + (uint32_t)(h * NG)) % SST]);
         }
-        if (k >= SST) wait_wd<2000>(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k);
-        store_planes(sv4, cv4, sm.S + ss * S_STAGE + soff);
+#pragma unroll
+        for (int h = 0; h < NB; ++h) {
+          if (h < nb) {
+            const uint32_t k = k0 + (uint32_t)h, ss = k % SST;
+            if (k >= SST) wait_wd<2000>(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k);
+            store_planes(svv[h], cvv[h], sm.S + ss * S_STAGE + soff);
+          }
+        }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
-        if (pw == 0 && lane == 0) FFP_TRACE(5, k);   // planes of stage k stored
-        pend = (int)ss;
+        if (pw == 0 && lane == 0) FFP_TRACE(5, k0);   // planes of the batch stored
+        pend_k = k0;
+        pend_n = nb;
       }
       kbase += (uint32_t)nst;
       // the two sums of frequency f: over the 8 lanes that share it (lane bits 2..4), then published per group
@@ -682,7 +709,8 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       if (lane == 0) mbar_arrive(&sm.sums_full[buf]);
     }
     __syncwarp();
-    if (lane == 0 && pend >= 0) mbar_arrive(&sm.s_full[pend]);  // the last stage of this CTA
+    if (lane == 0)  // the last stages of this CTA
+      for (int h = 0; h < pend_n; ++h) mbar_arrive(&sm.s_full[(pend_k + (uint32_t)(h * NG)) % SST]);
   }
   tc_fence_before();
   __syncthreads();
@@ -862,14 +890,17 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   const size_t smem = (size_t)gst * a.gslot + SMEM_FIXED;
   static bool attr_done[64] = {};
   if (!attr_done[pk->device & 63]) {
-    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define FFP_I8_ATTR(NPW_, NB_)                                                                                             \
+  FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false, NPW_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+  FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true, NPW_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FFP_I8_ATTR(16, 1) FFP_I8_ATTR(8, 1) FFP_I8_ATTR(8, 2)
+#undef FFP_I8_ATTR
     attr_done[pk->device & 63] = true;
   }
   const unsigned grid = (unsigned)(nwork < pk->num_sms ? nwork : pk->num_sms);
-  // producer warps per CTA: a tuning knob while the kernel is being brought up (both variants compute the same bits)
+  // producer warps per CTA and stages per producer batch: tuning knobs kept for experiments (FASTFP_B200_I8_NPW = 8 | 16,
+  // FASTFP_B200_I8_NB = 1 | 2 with 8 warps, FASTFP_B200_I8_EXCL = 1: fp64 parts wait for the tensor pipe to drain);
+  // every variant computes the same bits per (pulsar, frequency) up to the order of the producers' fp64 sums
 #ifdef FFP_I8_TRACE
   long long* d_trace = nullptr;
   const char* trace_path = getenv("FASTFP_B200_I8_TRACE");
@@ -882,13 +913,19 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   static const int excl = getenv("FASTFP_B200_I8_EXCL") ? atoi(getenv("FASTFP_B200_I8_EXCL")) : 0;
   a.excl = excl;
   static const int npw = getenv("FASTFP_B200_I8_NPW") ? atoi(getenv("FASTFP_B200_I8_NPW")) : 16;
-  if (npw == 16) {
-    if (nm) fp_sweep_i8_kernel<true, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
-    else fp_sweep_i8_kernel<false, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
-  } else {
-    if (nm) fp_sweep_i8_kernel<true, 8><<<grid, Roles<8>::THREADS, smem, st>>>(a);
-    else fp_sweep_i8_kernel<false, 8><<<grid, Roles<8>::THREADS, smem, st>>>(a);
-  }
+  static const int nbatch = getenv("FASTFP_B200_I8_NB") ? atoi(getenv("FASTFP_B200_I8_NB")) : 1;
+#define FFP_I8_LAUNCH(NPW_, NB_)                                                                    \
+  do {                                                                                              \
+    if (nm) fp_sweep_i8_kernel<true, NPW_, NB_><<<grid, Roles<NPW_>::THREADS, smem, st>>>(a);       \
+    else fp_sweep_i8_kernel<false, NPW_, NB_><<<grid, Roles<NPW_>::THREADS, smem, st>>>(a);         \
+  } while (0)
+  // batches of NB stages need the G ring to stay ahead of the delayed announcements (2 NB - 1 slots at least)
+  // (measured on C2: 8 warps x batches of 1 / 2 / 3 stages 19.5 / 19.3 / 20.8 ms, 16 warps in two groups 18.1 ms = default)
+  const int nb_eff = npw == 16 ? 1 : (nbatch >= 2 && gst >= 3 ? 2 : 1);
+  if (npw == 16) FFP_I8_LAUNCH(16, 1);
+  else if (nb_eff == 2) FFP_I8_LAUNCH(8, 2);
+  else FFP_I8_LAUNCH(8, 1);
+#undef FFP_I8_LAUNCH
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
 #ifdef FFP_I8_TRACE
