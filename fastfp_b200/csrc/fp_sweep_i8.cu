@@ -78,7 +78,6 @@ struct Args {
   int mvpad;
   int ntile, nwork;
   int gslot, gst;                // G ring: bytes per slot (7 x rows_max x 32), number of slots
-  int excl;                      // 1: fp64 parts wait for the tensor pipe to drain (see the producers)
 #ifdef FFP_I8_TRACE
   long long* trace;              // [TRACE_EV][TRACE_K] clock64 of CTA 0's first stages (tools/i8_trace.py)
 #endif
@@ -310,9 +309,8 @@ struct Smem {
 constexpr size_t SMEM_FIXED = (size_t)SST * S_STAGE + VST * V_STAGE + (2 * 2 * NF * 3 + 4 * NF * 3 + NF * 2) * 8 +
                               (8 + 8 + 2 * VST + 2 * SST + 2 + 4) * 8 + 16;
 
-template <bool NMFP, int NPW, int NB>
+template <bool NMFP, int NPW>
 __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(const Args ar) {
-  static_assert(NB == 1 || NPW == 8, "batches of several stages: one producer group (registers)");
   using R = Roles<NPW>;
   constexpr int NG = R::NG;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -569,11 +567,12 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
     const int soff = swz32(f, 4 * kg);                 // word of TOAs 4kg..4kg+3 in row f (sin); cos row: + 1024
     // The schedule is built around one hardware fact: fp64 arithmetic and tcgen05 MMAs share a resource on the SM
     // (tools/probes/umma_fp64_overlap_probe.cu: back-to-back MMAs starve DFMAs; tools/i8_trace.py: next to each other
-    // both run at ~80% of their combined rate, and a warp stalled on the fp64 pipe cannot issue its integer work
-    // either). Everything else (conversions, integer, stores) is free underneath the MMAs. So the two are kept apart:
-    //   fp64 part of stage k (A_k)  starts when the MMAs of stage k - NG - 1 have completed (tensor pipe idle),
-    //   stage k - NG is announced (s_full) after A_k,  its MMAs then run next to the integer part B_k (digits, byte
-    //   transpose, stores),  and A_{k+NG} waits for them.
+    // the fp64 part of a stage runs at a quarter of the fp64 rate and the MMAs at ~70 %), and a warp stalled on the fp64
+    // pipe cannot issue its integer work either. Conversions, integer work and stores are free underneath the MMAs. So
+    // a group announces stage k (s_full) not when its planes are stored but after the fp64 part of its NEXT stage: the
+    // MMAs of stage k then start next to the integer part of stage k + NG (digits, byte transpose, stores) instead of
+    // next to an fp64 part. Measured alternatives (announce at once, integer part interleaved into the next fp64 part,
+    // strictly exclusive phases, batches and coarse phases of several stages): DESIGN.md section 4b.
     auto store_planes = [&](const double (&sv4)[4], const double (&cv4)[4], unsigned char* sb) {
       uint32_t slo[4], shi[4], clo[4], chi[4];
 #pragma unroll
@@ -611,10 +610,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       }
     };
     uint32_t kbase = 0, it = 0;
-    // stages whose planes are stored but not announced yet: pend_n consecutive stages of this group from pend_k on
-    uint32_t pend_k = 0;
-    int pend_n = 0;
-    const bool EXCL = ar.excl != 0;
+    int pend = -1;  // S slot whose planes are stored but not announced yet
     for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
       const int gp = item / ar.ntile, ft = item - gp * ar.ntile;
       const PulsarMeta pm = ar.meta[ar.pidx[gp]];
@@ -625,69 +621,50 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       double s3[2] = {0.0, 0.0};  // s N^-1 s, s N^-1 c
       const int nst = pm.i8_nst;
       const int c0 = NG == 1 ? 0 : (int)((kbase ^ grp) & 1u);
-      // NB stages per batch (NB > 1 with one producer group only): the fp64 parts of the batch back to back, then the
-      // announcement of the previous batch, then the integer parts -- every switch between fp64 work and MMAs costs a
-      // tensor-pipe fill and the fp64 part's latency-bound tail, a batch pays them once
-      for (int c = c0; c < nst; c += NG * NB) {
-        const uint32_t k0 = kbase + (uint32_t)c;
-        const int nb = NB == 1 ? 1 : min(NB, nst - c);
-        double svv[NB][4], cvv[NB][4];
-        if (pw == 0 && lane == 0) FFP_TRACE(3, k0);   // fp64 part of stage k0 starts
+      for (int c = c0; c < nst; c += NG) {
+        const uint32_t k = kbase + (uint32_t)c;
+        const uint32_t sv = k % VST, ss = k % SST;
+        wait_wd<2000>(&sm.v_full[sv], (k / VST) & 1u, 8, k);
+        const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
+        if (pw == 0 && lane == 0) FFP_TRACE(3, k);   // fp64 part of stage k starts (inputs present)
+        // ---- fp64 part: four (TOA, frequency) pairs per thread
+        double ph[4], ninv[4], sv4[4], cv4[4];
 #pragma unroll
-        for (int h = 0; h < NB; ++h) {
-          if (h < nb) {
-            const uint32_t k = k0 + (uint32_t)h;
-            const uint32_t sv = k % VST;
-            wait_wd<2000>(&sm.v_full[sv], (k / VST) & 1u, 8, k);
-            if (EXCL && h == 0 && k >= (uint32_t)(NG + 1)) {  // the tensor pipe has drained: MMAs complete in order
-              const uint32_t j = k - (uint32_t)(NG + 1);
-              wait_wd<2000>(&sm.s_empty[j % SST], (j / SST) & 1u, 12, k);
-            }
-            const double2* vv = reinterpret_cast<const double2*>(sm.V + sv * V_STAGE) + 4 * kg;
-            double ph[4], ninv[4];
+        for (int e = 0; e < 4; ++e) {
+          const double2 tn = vv[e];                    // (t, 1/N)
+          ph[e] = __dmul_rn(omega, tn.x);              // ((2*pi)*f)*t, rounded once more
+          ninv[e] = tn.y;
+        }
+        if (fast) {
+          sincos_cw_n<4>(ph, sv4, cv4);  // in lockstep: phases inside the Cody-Waite range (checked once per item)
+        } else {
+          // cold: some phase of this item may exceed the Cody-Waite range (or is NaN/Inf): library sincos
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const double2 tn = vv[e];                    // (t, 1/N)
-              ph[e] = __dmul_rn(omega, tn.x);              // ((2*pi)*f)*t, rounded once more
-              ninv[e] = tn.y;
-            }
-            if (fast) {
-              sincos_cw_n<4>(ph, svv[h], cvv[h]);  // in lockstep: phases inside the Cody-Waite range (checked per item)
-            } else {
-              // cold: some phase of this item may exceed the Cody-Waite range (or is NaN/Inf): library sincos
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {  // unrolled: a dynamic index would put the arrays in local memory
-                double s1, c1;
-                sincos(ph[e], &s1, &c1);
-                svv[h][e] = s1; cvv[h][e] = c1;
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const double sn = svv[h][e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
-              s3[0] = fma(sn, svv[h][e], s3[0]);
-              s3[1] = fma(sn, cvv[h][e], s3[1]);
-            }
+          for (int e = 0; e < 4; ++e) {  // unrolled: a dynamic index would put the arrays in local memory
+            double s1, c1;
+            sincos(ph[e], &s1, &c1);
+            sv4[e] = s1; cv4[e] = c1;
           }
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double sn = sv4[e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
+          s3[0] = fma(sn, sv4[e], s3[0]);
+          s3[1] = fma(sn, cv4[e], s3[1]);
+        }
+        // ---- the group's previous stage is complete in shared memory: announce it now (see above)
         __syncwarp();
         if (lane == 0) {
-          if (pw == 0) FFP_TRACE(4, k0);              // fp64 parts of the batch done
-          for (int h = 0; h < nb; ++h) mbar_arrive(&sm.v_empty[(k0 + (uint32_t)h) % VST]);
-          for (int h = 0; h < pend_n; ++h) mbar_arrive(&sm.s_full[(pend_k + (uint32_t)(h * NG)) % SST]);
+          if (pw == 0) FFP_TRACE(4, k);              // fp64 part of stage k done
+          mbar_arrive(&sm.v_empty[sv]);
+          if (pend >= 0) mbar_arrive(&sm.s_full[pend]);
         }
-#pragma unroll
-        for (int h = 0; h < NB; ++h) {
-          if (h < nb) {
-            const uint32_t k = k0 + (uint32_t)h, ss = k % SST;
-            if (k >= SST) wait_wd<2000>(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k);
-            store_planes(svv[h], cvv[h], sm.S + ss * S_STAGE + soff);
-          }
-        }
+        // ---- integer part: digits, 4 x 7 byte transpose, stores
+        if (k >= SST) wait_wd<2000>(&sm.s_empty[ss], ((k / SST) - 1) & 1u, 9, k);
+        store_planes(sv4, cv4, sm.S + ss * S_STAGE + soff);
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
-        if (pw == 0 && lane == 0) FFP_TRACE(5, k0);   // planes of the batch stored
-        pend_k = k0;
-        pend_n = nb;
+        if (pw == 0 && lane == 0) FFP_TRACE(5, k);   // planes of stage k stored
+        pend = (int)ss;
       }
       kbase += (uint32_t)nst;
       // the two sums of frequency f: over the 8 lanes that share it (lane bits 2..4), then published per group
@@ -709,8 +686,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       if (lane == 0) mbar_arrive(&sm.sums_full[buf]);
     }
     __syncwarp();
-    if (lane == 0)  // the last stages of this CTA
-      for (int h = 0; h < pend_n; ++h) mbar_arrive(&sm.s_full[(pend_k + (uint32_t)(h * NG)) % SST]);
+    if (lane == 0 && pend >= 0) mbar_arrive(&sm.s_full[pend]);  // the group's last stage of this CTA
   }
   tc_fence_before();
   __syncthreads();
@@ -890,17 +866,15 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   const size_t smem = (size_t)gst * a.gslot + SMEM_FIXED;
   static bool attr_done[64] = {};
   if (!attr_done[pk->device & 63]) {
-#define FFP_I8_ATTR(NPW_, NB_)                                                                                             \
-  FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false, NPW_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-  FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true, NPW_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FFP_I8_ATTR(16, 1) FFP_I8_ATTR(8, 1) FFP_I8_ATTR(8, 2)
+#define FFP_I8_ATTR(NPW_)                                                                                             \
+  FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<false, NPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+  FFP_CUDA(cudaFuncSetAttribute(fp_sweep_i8_kernel<true, NPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FFP_I8_ATTR(16) FFP_I8_ATTR(8)
 #undef FFP_I8_ATTR
     attr_done[pk->device & 63] = true;
   }
   const unsigned grid = (unsigned)(nwork < pk->num_sms ? nwork : pk->num_sms);
-  // producer warps per CTA and stages per producer batch: tuning knobs kept for experiments (FASTFP_B200_I8_NPW = 8 | 16,
-  // FASTFP_B200_I8_NB = 1 | 2 with 8 warps, FASTFP_B200_I8_EXCL = 1: fp64 parts wait for the tensor pipe to drain);
-  // every variant computes the same bits per (pulsar, frequency) up to the order of the producers' fp64 sums
+  // producer warps per CTA: 16 (two groups alternating stages; default, C2 18.0 ms) or 8 (FASTFP_B200_I8_NPW=8: 19.2 ms)
 #ifdef FFP_I8_TRACE
   long long* d_trace = nullptr;
   const char* trace_path = getenv("FASTFP_B200_I8_TRACE");
@@ -910,22 +884,14 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   }
   a.trace = d_trace;
 #endif
-  static const int excl = getenv("FASTFP_B200_I8_EXCL") ? atoi(getenv("FASTFP_B200_I8_EXCL")) : 0;
-  a.excl = excl;
   static const int npw = getenv("FASTFP_B200_I8_NPW") ? atoi(getenv("FASTFP_B200_I8_NPW")) : 16;
-  static const int nbatch = getenv("FASTFP_B200_I8_NB") ? atoi(getenv("FASTFP_B200_I8_NB")) : 1;
-#define FFP_I8_LAUNCH(NPW_, NB_)                                                                    \
-  do {                                                                                              \
-    if (nm) fp_sweep_i8_kernel<true, NPW_, NB_><<<grid, Roles<NPW_>::THREADS, smem, st>>>(a);       \
-    else fp_sweep_i8_kernel<false, NPW_, NB_><<<grid, Roles<NPW_>::THREADS, smem, st>>>(a);         \
-  } while (0)
-  // batches of NB stages need the G ring to stay ahead of the delayed announcements (2 NB - 1 slots at least)
-  // (measured on C2: 8 warps x batches of 1 / 2 / 3 stages 19.5 / 19.3 / 20.8 ms, 16 warps in two groups 18.1 ms = default)
-  const int nb_eff = npw == 16 ? 1 : (nbatch >= 2 && gst >= 3 ? 2 : 1);
-  if (npw == 16) FFP_I8_LAUNCH(16, 1);
-  else if (nb_eff == 2) FFP_I8_LAUNCH(8, 2);
-  else FFP_I8_LAUNCH(8, 1);
-#undef FFP_I8_LAUNCH
+  if (npw == 16) {
+    if (nm) fp_sweep_i8_kernel<true, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
+    else fp_sweep_i8_kernel<false, 16><<<grid, Roles<16>::THREADS, smem, st>>>(a);
+  } else {
+    if (nm) fp_sweep_i8_kernel<true, 8><<<grid, Roles<8>::THREADS, smem, st>>>(a);
+    else fp_sweep_i8_kernel<false, 8><<<grid, Roles<8>::THREADS, smem, st>>>(a);
+  }
   g_launches += 1;
   FFP_CUDA(cudaGetLastError());
 #ifdef FFP_I8_TRACE
