@@ -520,6 +520,10 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
         nst = -(-wl["n"] // 32)
         items = wl["P"] * -(-(hi - lo) // 32)
         exec_top = items * nst * 28.0 * 2.0 * 128 * 64 * 32 / (kern_ms * 1e-3) / 1e12
+        rows_pad = 32 * -(-(M_BASIS + 1) // 32)
+        smem_stage = 28.0 * 6144 + 7.0 * rows_pad * 32 + 14336
+        sm_count = torch.cuda.get_device_properties(ctx.local).multi_processor_count
+        smem_peak = 128.0 * sm_count * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0) * 1e6 / 1e9
         roofline = {
             "bound": "tensor", "pipe": "INT8 tensor path (tcgen05.mma kind::i8, int32 accumulators in tensor memory)",
             "achieved": ach_top, "peak": i8_peak, "unit": "TOP/s", "frac": ach_top / i8_peak,
@@ -534,6 +538,13 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
                                     "of operands from shared memory = 48 cycles at 128 B/clk, against 32 cycles of tensor "
                                     "time -- shared-memory operand bandwidth is what binds this formulation (TMEM holds "
                                     "7 accumulators x 64 columns, so N cannot grow)"},
+            "smem_bound": {
+                "achieved": items * nst * smem_stage / (kern_ms * 1e-3) / 1e9, "peak": smem_peak, "unit": "GB/s",
+                "frac": items * nst * smem_stage / (kern_ms * 1e-3) / 1e9 / smem_peak, "bytes_per_stage": smem_stage,
+                "note": "shared-memory traffic of one 32-TOA x 32-frequency stage (28 MMAs x 6 KB of operand reads, the TMA "
+                        "write of the G planes, the producers' 14 KB of sin/cos planes) against 128 B/clk/SM at the sampled "
+                        "SM clock: the floor of this formulation; the rest of the step is the fp64 sin/cos work, which "
+                        "shares a resource with the MMAs on the SM (DESIGN.md 4b)"},
             "fp64_equivalent": {"achieved": ach_tf, "unit": "TFLOP/s", "fp64_pipe_peak": fp64_peak,
                                 "ratio": ach_tf / fp64_peak,
                                 "note": "the same statistic in fp64 flops (4m+10)n per eval against the fp64 pipe peak the "

@@ -1,0 +1,56 @@
+"""GPU tests at the limits of the tensor-core sweep (fp_sweep_i8.cu): the widest basis and the longest pulsar it
+takes (m = 127 -> all 128 operand rows, n = 16384 -> the int32 accumulators' exactness bound), the narrowest one,
+and the hand-over to the fp64 kernel just outside. Run with -m gpu on a B200."""
+import numpy as np
+import pytest
+
+import fastfp_b200
+from conftest import EPS, term_tolerance
+from fastfp_b200 import _cabi, synth
+from oracle import fp_oracle as o
+from oracle import truth
+
+pytestmark = pytest.mark.gpu
+
+
+def _against_truth(pta, freqs, path):
+    mats = (pta.Nvecs, pta.Ts, pta.sigmas)
+    fp = fastfp_b200.FastFp(pta.psrs, path=path)
+    assert fp.prepare(*mats).path == path
+    got = fp.per_pulsar_terms(freqs, *mats)
+    args = (freqs, pta.toas, pta.residuals, *mats)
+    ora = o.fp_sweep(*args, per_pulsar=True)
+    tt, cond = truth.fp_sweep_truth(*args)
+    tol = term_tolerance(tt.astype(float), cond, ora)
+    defined = EPS * cond < 0.05 * np.abs(tt.astype(float))
+    assert defined.mean() > 0.9
+    ratio = np.where(defined, np.abs(got - tt.astype(float)) / tol, 0.0)
+    assert np.all(ratio <= 1), f"{path}: worst |got - truth| / tol = {ratio.max():.3g}"
+    return got
+
+
+def test_widest_basis_and_longest_pulsar_the_tensor_path_takes():
+    # m = 7 + 2 * 60 = 127 columns (+ the C^-1 r row = 128 operand rows); 16384 TOAs = 512 stages
+    pta = synth.make_pta(2, [16384, 4099], n_tm=[7, 7], ncomps=60, seed=31)
+    assert pta.Ts[0].shape == (16384, 127)
+    freqs = np.concatenate((synth.fp_freqs(30), np.array([1.0, 17.5, 60.0]) / pta.Tspan))  # 33 bins: ragged tile
+    t8 = _against_truth(pta, freqs, "i8")
+    t64 = _against_truth(pta, freqs, "fp64")
+    np.testing.assert_allclose(t8.sum(axis=0), t64.sum(axis=0), rtol=1e-6)  # same statistic from both kernels
+
+
+def test_one_toa_or_one_column_too_many_hands_over_to_the_fp64_kernel():
+    for ns, n_tm in (([16385, 300], [7, 7]), ([500, 300], [8, 7])):
+        pta = synth.make_pta(2, ns, n_tm=n_tm, ncomps=60, seed=32)
+        mats = (pta.Nvecs, pta.Ts, pta.sigmas)
+        assert fastfp_b200.FastFp(pta.psrs).prepare(*mats).path == "fp64"        # auto
+        assert fastfp_b200.FastFp(pta.psrs, path="prefer-i8").prepare(*mats).path == "fp64"
+        with pytest.raises(_cabi.FastFpError):
+            fastfp_b200.FastFp(pta.psrs, path="i8").prepare(*mats)
+
+
+def test_narrowest_basis_and_shortest_pulsars():
+    # one timing-model column, white noise only: 2 real operand rows of 128; 33 and 1 TOAs: a partial first stage
+    pta = synth.make_pta(3, [33, 32, 7], n_tm=1, white_only=True, seed=33)
+    freqs = synth.fp_freqs(65)
+    _against_truth(pta, freqs, "i8")
