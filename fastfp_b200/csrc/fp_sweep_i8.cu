@@ -222,9 +222,8 @@ __device__ __forceinline__ uint2 digits7(double x) {
   return make_uint2((uint32_t)U ^ 0x80808080u, (uint32_t)((unsigned long long)U >> 32) ^ 0x00808080u);
 }
 
-// Every wait of this kernel is bounded: a protocol error would otherwise hang the GPU. No legitimate wait is longer
-// than a few stages (microseconds); after ~2 s of polling the CTA reports where it was stuck and traps, which the
-// host sees as a launch failure instead of a hung device.
+// Every wait of this kernel is bounded (wait_wd below): a protocol error would otherwise hang the GPU; a timed-out wait
+// reports where it was stuck and traps, which the host sees as a launch failure instead of a hung device.
 __device__ __forceinline__ void wait_timeout(int tag, uint32_t k) {
   printf("[fastfp_b200 i8 sweep] mbarrier wait timed out: tag %d, stage/item %u, block %d, warp %d\n", tag, k,
          (int)blockIdx.x, (int)(threadIdx.x >> 5));
@@ -243,15 +242,26 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));  // volatile: stays inside the branch that asks for it
+  return t;
+}
 // SLEEP_NS = 0: the waiter is on the critical path and polls with the default time slice; otherwise each poll may
-// suspend the warp for up to SLEEP_NS, so that waiting warps do not spend issue slots the producers need.
+// suspend the warp for up to SLEEP_NS, so that waiting warps do not spend issue slots the producers need. Bounded: no
+// legitimate wait is longer than one item (< 1 ms); after 5 s on the global timer (looked at every 256 polls) the CTA
+// reports where it was stuck and traps.
 template <int SLEEP_NS>
 __device__ __forceinline__ void wait_wd(uint64_t* bar, uint32_t parity, int tag, uint32_t k) {
   if (mbar_try_wait(bar, parity)) return;
-  constexpr uint32_t LIMIT = 1u << 28;   // >= 2 s at the shortest poll observed (~ 20 ns)
   uint32_t n = 0;
+  unsigned long long t0 = 0;
   while (!(SLEEP_NS ? mbar_try_wait_hint(bar, parity, (uint32_t)SLEEP_NS) : mbar_try_wait(bar, parity))) {
-    if (++n > LIMIT) wait_timeout(tag, k);
+    if ((++n & 255u) == 0) {
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 5000000000ULL) wait_timeout(tag, k);
+    }
   }
 }
 __device__ __forceinline__ bool elect_one() {
