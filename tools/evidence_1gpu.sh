@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 evidence run on one B200: bench lines, reference arm, ncu launch lists (+ DRAM bytes), one full capture
+# round-2 evidence run on one B200 (tools/evidence_1gpu.sh): bench lines, reference arm, ncu launch lists (+ DRAM bytes), one full capture
 O=gpurun_out
 mkdir -p $O
 echo "== default bench (C4 + secondaries + cpu baseline)"

@@ -7,6 +7,9 @@ pta = synth.make_pta(2, [700, 333], n_tm=[12, 9], ncomps=30, seed=3)
 f = synth.fp_freqs(70)
 fp = fastfp_b200.FastFp(pta.psrs)
 a = fp(f, pta.Nvecs, pta.Ts, pta.sigmas)
+print("sweep path:", fp.prepare(pta.Nvecs, pta.Ts, pta.sigmas).path)   # auto: the tensor-core kernel for this pack
+a64 = fastfp_b200.FastFp(pta.psrs, path="fp64")(f, pta.Nvecs, pta.Ts, pta.sigmas)
+print("max rel dev between the two kernels:", float(np.nanmax(np.abs(a / a64 - 1))))
 curn = CURN_container(pta.Ffreqs[:10])
 sigs = [RN_container(q, Ffreqs=pta.Ffreqs, add_curn=True, curn_container=curn) for q in pta.psrs]
 b = NMFP(pta.psrs, sigs)(f[:40], synth.draw_samples(pta, 9), pta.Nvecs, pta.Ts, pta.TNTs)
