@@ -617,13 +617,13 @@ def run_nmfp(key, wl, ctx, steps, warmup, with_cpu_baseline):
     mine = {k: v[lo:hi] for k, v in samples.items()}  # this rank's draws (the reference's host dict)
 
     def step_device():
-        return parallel.sharded_draws(lambda a, b: nm(freqs_dev, mine, *mats), D_total)
+        return parallel.sharded_draws(lambda a, b: nm.calculate_nmfp_2d(freqs_dev, mine, *mats), D_total)
 
     out_pinned = torch.empty((D_total, F), dtype=torch.float64).pin_memory()
 
     def step_e2e():
         f = freqs_host.to(dev, non_blocking=True)
-        full = parallel.sharded_draws(lambda a, b: nm(f, mine, *mats), D_total)
+        full = parallel.sharded_draws(lambda a, b: nm.calculate_nmfp_2d(f, mine, *mats), D_total)
         out_pinned.copy_(full, non_blocking=True)
         return out_pinned
 
@@ -717,7 +717,10 @@ def run_nmfp(key, wl, ctx, steps, warmup, with_cpu_baseline):
         "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_of(key, wl, world),
         "run": {"parallelism": f"draw-shard x{world} ({hi - lo} draws on rank 0), pulsar arrays replicated, one NCCL "
-                               f"all-gather of the (D, F) rows ({8 * F * (hi - lo) / 1e6:.1f} MB per rank)",
+                               f"all-gather of the (D, F) rows ({8 * F * (hi - lo) / 1e6:.1f} MB per rank)" +
+                               ("; the draw-independent stage A is sharded over the frequency tiles and its outputs "
+                                "all-gathered (two NCCL all-gathers per step) instead of being repeated on every rank"
+                                if world > 1 else ""),
                 "l2": "256 MiB buffer written between timed steps (L2 flush)",
                 "inputs": "frequencies resident in HBM; the noise draws are the reference's host dict of "
                           f"(D,) arrays ({8 * (2 * wl['P'] + 2) * (hi - lo)} bytes per GPU), uploaded inside "

@@ -41,6 +41,12 @@ SYMBOLS = {
         [C.c_int, C.c_int, c_int64_p, c_int64_p, c_double_pp, c_double_pp, c_double_pp, c_double_pp,
          c_double_pp, c_int64_p, c_double_pp, C.c_void_p, C.POINTER(C.c_void_p)],
     ),
+    "fastfp_nmfp_tile_sizes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fastfp_nmfp_stage_a": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fastfp_nmfp_stage_b": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
+    ),
     "fastfp_nmfp_sweep": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p],
@@ -389,6 +395,23 @@ class Pack:
             flags |= OUT_ON_DEVICE
         check(lib.fastfp_nmfp_sweep(self._h, _vp(fptr), F, _vp(pptr), D, _vp(optr), flags, C.c_void_p(stream)))
         return ret
+
+    # the two halves of nmfp_sweep as separate calls (device pointers only): parallel.py shards them in two dimensions
+    def nmfp_tile_sizes(self):
+        """doubles per 32-frequency tile (all pulsars) of the two stage-A outputs"""
+        z, a = C.c_int64(0), C.c_int64(0)
+        check(load().fastfp_nmfp_tile_sizes(self._h, C.byref(z), C.byref(a)))
+        return int(z.value), int(a.value)
+
+    def nmfp_stage_a(self, freqs_ptr: int, F: int, z_ptr: int, a_ptr: int, stream: int = 0):
+        check(load().fastfp_nmfp_stage_a(self._h, C.c_void_p(freqs_ptr), F, C.c_void_p(z_ptr), C.c_void_p(a_ptr),
+                                         C.c_void_p(stream)))
+
+    def nmfp_stage_b(self, freqs_ptr: int, F: int, z_ptr: int, a_ptr: int, tiles_per_block: int, phiinv_ptr: int,
+                     D: int, out_ptr: int, stream: int = 0):
+        check(load().fastfp_nmfp_stage_b(self._h, C.c_void_p(freqs_ptr), F, C.c_void_p(z_ptr), C.c_void_p(a_ptr),
+                                         tiles_per_block, C.c_void_p(phiinv_ptr), D, C.c_void_p(out_ptr),
+                                         C.c_void_p(stream)))
 
     def powerlaw_phiinv(self, Ffreqs, log10_A, gamma, curn_Ffreqs, curn_log10_A, curn_gamma, out_dev, stream=0):
         """Device-side ``get_phiinv`` of the varying block for D draws (host params in)."""

@@ -30,16 +30,6 @@ struct DeviceGuard {
   }
 };
 
-template <typename T>
-static int ensure(T** buf, int64_t* cap, int64_t need) {
-  if (*cap >= need) return 0;
-  if (*buf) cudaFree(*buf);
-  *buf = nullptr;
-  *cap = 0;
-  FFP_CUDA(cudaMalloc(buf, (size_t)need * sizeof(T)));
-  *cap = need;
-  return 0;
-}
 
 // nmfp.cu
 int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res,
@@ -47,6 +37,9 @@ int nmfp_pack_finish(fastfp_pack* pk, const double* d_toas, const double* d_res,
                      const double* d_phiinv_fix, cudaStream_t st, const BlockNDev* bn = nullptr);
 int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F,
                     const double* d_phiinv_var, int64_t D, double* d_out, cudaStream_t st);
+int nmfp_stage_a_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* dZ, double* dA, cudaStream_t st);
+int nmfp_stage_b_only(const fastfp_pack* pk, const double* d_freqs, int64_t F, const double* dZ, const double* dA,
+                      int nt_blk, const double* d_phiinv_var, int64_t D, double* d_out, cudaStream_t st);
 int powerlaw_phiinv_impl(const fastfp_pack* pk, const double* const* Ffreqs, const double* log10_A,
                          const double* gamma, int64_t D, const double* curn_Ffreqs, int64_t ncurn,
                          const double* curn_log10_A, const double* curn_gamma, double* out,
@@ -175,7 +168,7 @@ static void pack_free(fastfp_pack* pk) {
   for (auto& gr : pk->groups) cudaFree(gr.d_pidx);
   cudaFree(pk->d_meta); cudaFree(pk->d_packets); cudaFree(pk->d_L); cudaFree(pk->d_info);
   cudaFree(pk->d_S0); cudaFree(pk->d_zr); cudaFree(pk->d_slab); cudaFree(pk->d_counter); cudaFree(pk->d_done_mask);
-  cudaFree(pk->d_terms); cudaFree(pk->d_freqs); cudaFree(pk->d_out); cudaFree(pk->d_scratch);
+  cudaFree(pk->d_terms); cudaFree(pk->d_freqs); cudaFree(pk->d_out); cudaFree(pk->d_scratch); cudaFree(pk->d_lf);
   cudaFree(pk->d_pl); cudaFreeHost(pk->h_pl);
   cudaFree(pk->d_i8); cudaFree(pk->d_i8_scale); cudaFree(pk->d_pidx_all); cudaFree(pk->d_inner);
   if (pk->pl_event) cudaEventDestroy(pk->pl_event);
@@ -532,6 +525,37 @@ int fastfp_nmfp_sweep(const fastfp_pack_t* pk, const double* freqs, int64_t F,
   }
   if (d_phi_tmp) { cudaStreamSynchronize(st); cudaFree(d_phi_tmp); }
   return rc;
+}
+
+int fastfp_nmfp_tile_sizes(const fastfp_pack_t* pk, int64_t* z_per_tile, int64_t* a_per_tile) {
+  if (!pk || !pk->nmfp || !z_per_tile || !a_per_tile) { set_error("fastfp_nmfp_tile_sizes: not an nmfp pack"); return FASTFP_ERR_INVALID; }
+  *z_per_tile = (int64_t)pk->P * pk->mvpad * 64;
+  *a_per_tile = (int64_t)pk->P * 160;
+  return FASTFP_OK;
+}
+
+int fastfp_nmfp_stage_a(const fastfp_pack_t* pk, const double* freqs_dev, int64_t F, double* z_dev, double* a_dev,
+                        void* stream) {
+  if (!pk || !pk->nmfp || F <= 0 || !freqs_dev || !z_dev || !a_dev) {
+    set_error("fastfp_nmfp_stage_a: not an nmfp pack, null argument or F <= 0");
+    return FASTFP_ERR_INVALID;
+  }
+  DeviceGuard g(pk->device);
+  return nmfp_stage_a_impl(pk, freqs_dev, F, z_dev, a_dev, (cudaStream_t)stream);
+}
+
+int fastfp_nmfp_stage_b(const fastfp_pack_t* pk, const double* freqs_dev, int64_t F, const double* z_dev,
+                        const double* a_dev, int64_t tiles_per_block, const double* phiinv_var_dev, int64_t D,
+                        double* out_dev, void* stream) {
+  if (!pk || !pk->nmfp || F <= 0 || D < 0 || tiles_per_block <= 0 || !freqs_dev || !z_dev || !a_dev ||
+      (D > 0 && (!phiinv_var_dev || !out_dev))) {
+    set_error("fastfp_nmfp_stage_b: not an nmfp pack, null argument or bad size");
+    return FASTFP_ERR_INVALID;
+  }
+  if (D == 0) return FASTFP_OK;
+  DeviceGuard g(pk->device);
+  return nmfp_stage_b_only(pk, freqs_dev, F, z_dev, a_dev, (int)tiles_per_block, phiinv_var_dev, D, out_dev,
+                           (cudaStream_t)stream);
 }
 
 int fastfp_nmfp_stage_timing(fastfp_pack_t* pk, int enable) {

@@ -160,8 +160,10 @@ struct fastfp_pack {
   mutable int64_t freqs_cap = 0;
   mutable double* d_out = nullptr;
   mutable int64_t out_cap = 0;
-  mutable double* d_scratch = nullptr;
+  mutable double* d_scratch = nullptr;  // nmfp: stage-A tiles of a frequency batch
   mutable int64_t scratch_cap = 0;
+  mutable double* d_lf = nullptr;       // nmfp: L^-1 fragments of a draw batch
+  mutable int64_t lf_cap = 0;
   mutable double* d_inner = nullptr;   // Fe-statistic: inner products of a frequency batch + antenna patterns
   mutable int64_t inner_cap = 0;
   // staging of the per-draw power-law parameters (fastfp_powerlaw_phiinv): device + pinned host copy,
@@ -187,6 +189,18 @@ int cuda_fail(cudaError_t e, const char* what);
     cudaError_t e__ = (call);                                  \
     if (e__ != cudaSuccess) return ffp::cuda_fail(e__, #call); \
   } while (0)
+
+// grow-on-demand device scratch (contents are not preserved)
+template <typename T>
+inline int ensure(T** buf, int64_t* cap, int64_t need) {
+  if (*cap >= need) return 0;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  FFP_CUDA(cudaMalloc(buf, (size_t)need * sizeof(T)));
+  *cap = need;
+  return 0;
+}
 
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------
 // precompute.cu

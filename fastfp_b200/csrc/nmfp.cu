@@ -421,6 +421,8 @@ struct StageBArgs {
   double* out;           // [D][F]  (this launch writes rows d0 .. d0+Db-1)
   int64_t F, out_ld;
   int P, nt32, Db, lfw;
+  int nt_blk;            // Z and A hold blocks of nt_blk tiles: [block][P][nt_blk] (one block = nt32 when they were made here;
+                         // one block per rank when the tiles were made frequency-sharded and all-gathered)
 };
 
 // One CTA = NH half-tiles of 32 frequencies x NB_DT draws, all pulsars. 8*NH consumer warps (4
@@ -475,10 +477,9 @@ __global__ void __launch_bounds__(StageBCfg<NMBV>::THREADS, 1) nmfp_stageB_kerne
         const int buf = p % ZBUF;
         if (p >= ZBUF) mbar_wait(&zempty[buf], ((p / ZBUF) - 1) & 1);
         mbar_expect_tx(&zfull[buf], (uint32_t)(nh * (ZT + 160) * 8));
-        tma_load_1d(Zb + buf * NH * ZT, ar.Z + ((size_t)p * ar.nt32 + t32) * ZT, (uint32_t)(nh * ZT * 8),
-                    &zfull[buf]);
-        tma_load_1d(Ab + buf * NH * 160, ar.A + ((size_t)p * ar.nt32 + t32) * 160, (uint32_t)(nh * 160 * 8),
-                    &zfull[buf]);
+        const size_t tile = ((size_t)(t32 / ar.nt_blk) * ar.P + p) * ar.nt_blk + (size_t)(t32 % ar.nt_blk);
+        tma_load_1d(Zb + buf * NH * ZT, ar.Z + tile * ZT, (uint32_t)(nh * ZT * 8), &zfull[buf]);
+        tma_load_1d(Ab + buf * NH * 160, ar.A + tile * 160, (uint32_t)(nh * 160 * 8), &zfull[buf]);
       }
       const int s = it % NS;
       if (it >= NS) mbar_wait(&lempty[s], ((it / NS) - 1) & 1);
@@ -622,53 +623,75 @@ static int run_factor_and_stageB(const fastfp_pack* pk, const double* d_phiinv, 
   return 0;
 }
 
-int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, const double* d_phiinv_var,
-                    int64_t D, double* d_out, cudaStream_t st) {
+// Stage A alone: the z' tiles and a-terms of F frequencies into Z [P][ceil(F/32)][MV*64] and A [P][ceil(F/32)][160].
+int nmfp_stage_a_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* dZ, double* dA, cudaStream_t st) {
+  const int P = pk->P, MV = pk->mvpad;
+  const int nt32 = (int)((F + 31) / 32);
+  // stage-A tiles are written sparsely (rows of narrower pulsars, the tail of the last tile): clear
+  FFP_CUDA(cudaMemsetAsync(dZ, 0, (size_t)P * nt32 * (MV * 64) * 8, st));
+  FFP_CUDA(cudaMemsetAsync(dA, 0, (size_t)P * nt32 * 160 * 8, st));
+  NmfpOut nm{dZ, dA, MV};
+  // on the tensor path when the pack carries digit planes, else on the fp64 DMMA kernel
+  return pk->use_i8() ? launch_fp_sweep_i8(pk, d_freqs, F, nullptr, st, nullptr, &nm)
+                      : launch_fp_sweep(pk, d_freqs, F, nullptr, st, &nm);
+}
+
+// Factor + stage B for D draws on tiles that already exist: Z and A hold blocks of nt_blk tiles ([block][P][nt_blk]),
+// together the ceil(F/32) tiles of the F frequencies. out: (D, F) rows with leading dimension out_ld.
+int nmfp_stage_b_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, const double* dZ, const double* dA,
+                      int nt_blk, const double* d_phiinv_var, int64_t D, double* d_out, int64_t out_ld, cudaStream_t st,
+                      StageMarks& marks) {
   const int P = pk->P, MV = pk->mvpad, NMBV = MV / 8;
   const int lfw = linv_blocks(NMBV) * 32 + MV;
-  // frequency batches bound the stage-A outputs, draw batches the L^-1 store (~1.5 GiB each)
+  const int nt32 = (int)((F + 31) / 32);
+  if (nt_blk <= 0 || (nt_blk < nt32 && (nt_blk & 1))) {  // a CTA reads two consecutive tiles: never across blocks
+    set_error("stage B: tiles per block must be even when the tiles come in several blocks");
+    return FASTFP_ERR_INVALID;
+  }
+  // draw batches bound the L^-1 store (~1.5 GiB)
+  const int64_t DB = std::max<int64_t>(NB_DT, std::min<int64_t>(D, ((3LL << 26) / ((int64_t)P * lfw)) / NB_DT * NB_DT));
+  if (int rc = ensure(&pk->d_lf, &pk->lf_cap, DB * P * lfw)) return rc;
+  double* dLf = pk->d_lf;
+  for (int64_t dd = 0; dd < D; dd += DB) {
+    const int Db = (int)std::min(DB, D - dd);
+    StageBArgs sb{dZ, dA, dLf, d_freqs, pk->d_meta, d_out + dd * out_ld, F, out_ld, P, nt32, Db, lfw, nt_blk};
+    const double* ph = d_phiinv_var + dd * pk->mvar_total;
+    int rc;
+    if (NMBV == 4) rc = run_factor_and_stageB<4>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
+    else if (NMBV == 8) rc = run_factor_and_stageB<8>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
+    else if (NMBV == 12) rc = run_factor_and_stageB<12>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
+    else rc = run_factor_and_stageB<16>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int nmfp_stage_b_only(const fastfp_pack* pk, const double* d_freqs, int64_t F, const double* dZ, const double* dA,
+                      int nt_blk, const double* d_phiinv_var, int64_t D, double* d_out, cudaStream_t st) {
+  StageMarks marks;  // (stage timing is a facility of the combined sweep)
+  return nmfp_stage_b_impl(pk, d_freqs, F, dZ, dA, nt_blk, d_phiinv_var, D, d_out, F, st, marks);
+}
+
+int nmfp_sweep_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, const double* d_phiinv_var,
+                    int64_t D, double* d_out, cudaStream_t st) {
+  const int P = pk->P, MV = pk->mvpad;
+  // frequency batches bound the stage-A outputs (1 GiB)
   const int64_t per_f32 = (int64_t)P * (MV * 64 + 160);
   int64_t FB = std::max<int64_t>(32, ((1LL << 27) / std::max<int64_t>(1, per_f32)) * 32);
   FB = std::min<int64_t>(FB, (F + 31) / 32 * 32);
-  const int64_t DB = std::max<int64_t>(NB_DT, std::min<int64_t>(D, ((3LL << 26) / ((int64_t)P * lfw)) / NB_DT * NB_DT));
   const int64_t nt32_max = FB / 32;
-  const int64_t need = P * nt32_max * (int64_t)(MV * 64 + 160) + DB * P * lfw;
-  if (pk->scratch_cap < need) {
-    if (pk->d_scratch) cudaFree(pk->d_scratch);
-    pk->d_scratch = nullptr;
-    pk->scratch_cap = 0;
-    FFP_CUDA(cudaMalloc(&pk->d_scratch, (size_t)need * 8));
-    pk->scratch_cap = need;
-  }
+  if (int rc = ensure(&pk->d_scratch, &pk->scratch_cap, P * nt32_max * (int64_t)(MV * 64 + 160))) return rc;
   double* dZ = pk->d_scratch;
   double* dA = dZ + P * nt32_max * (int64_t)MV * 64;
-  double* dLf = dA + P * nt32_max * 160;
   StageMarks marks;
   marks.on = pk->time_stages;
   marks.mark(-1, st);
   for (int64_t f0 = 0; f0 < F; f0 += FB) {
     const int64_t Fb = std::min(FB, F - f0);
-    const int nt32 = (int)((Fb + 31) / 32);
-    // stage-A tiles are written sparsely (rows of narrower pulsars, the tail of the last tile): clear
-    FFP_CUDA(cudaMemsetAsync(dZ, 0, (size_t)P * nt32 * (MV * 64) * 8, st));
-    FFP_CUDA(cudaMemsetAsync(dA, 0, (size_t)P * nt32 * 160 * 8, st));
-    NmfpOut nm{dZ, dA, MV};
-    // stage A on the tensor path when the pack carries digit planes, else on the fp64 DMMA kernel
-    const bool i8 = pk->use_i8();
-    if (int rc = i8 ? launch_fp_sweep_i8(pk, d_freqs + f0, Fb, nullptr, st, nullptr, &nm)
-                    : launch_fp_sweep(pk, d_freqs + f0, Fb, nullptr, st, &nm)) return rc;
+    if (int rc = nmfp_stage_a_impl(pk, d_freqs + f0, Fb, dZ, dA, st)) return rc;
     marks.mark(0, st);
-    for (int64_t dd = 0; dd < D; dd += DB) {
-      const int Db = (int)std::min(DB, D - dd);
-      StageBArgs sb{dZ, dA, dLf, d_freqs + f0, pk->d_meta, d_out + dd * F + f0, Fb, F, P, nt32, Db, lfw};
-      const double* ph = d_phiinv_var + dd * pk->mvar_total;
-      int rc;
-      if (NMBV == 4) rc = run_factor_and_stageB<4>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
-      else if (NMBV == 8) rc = run_factor_and_stageB<8>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
-      else if (NMBV == 12) rc = run_factor_and_stageB<12>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
-      else rc = run_factor_and_stageB<16>(pk, ph, pk->mvar_total, Db, sb, dLf, st, marks);
-      if (rc) return rc;
-    }
+    if (int rc = nmfp_stage_b_impl(pk, d_freqs + f0, Fb, dZ, dA, (int)((Fb + 31) / 32), d_phiinv_var, D, d_out + f0, F, st,
+                                   marks)) return rc;
   }
   marks.finish(st, pk->stage_ms);
   return 0;

@@ -275,11 +275,9 @@ class NMFP(_PackCache):
                 raise ValueError("the common process must be the same CURN_container for every pulsar")
         return c0
 
-    def calculate_nmfp(self, fgw, samples, Nvecs, Ts, TNTs):
-        """Fp at ``fgw`` for the noise parameters ``samples`` (reference ``nmfp.py:76-119``)."""
-        import torch
-
-        lists = (Nvecs, Ts, TNTs)
+    def _draw_arrays(self, samples):
+        """The sample dictionary of the reference (``nmfp.py:82-92``) as ``(D, P)`` arrays of the red-noise
+        parameters, the common-process ones as ``(D,)`` (or None), the draw count and whether a draw axis was given."""
         P = len(self.rn_sigs)
         curn = self._curn_setup()
         names = [(s.rn_A_name, s.rn_gam_name) for s in self.rn_sigs]
@@ -294,6 +292,62 @@ class NMFP(_PackCache):
         G = np.stack([col(vals[2 * p + 1]) for p in range(P)], axis=1)   # (D, P)
         cA = col(vals[2 * P]) if curn is not None else None
         cG = col(vals[2 * P + 1]) if curn is not None else None
+        return curn, A, G, cA, cG, D, batched
+
+    def calculate_nmfp_2d(self, fgw, samples, Nvecs, Ts, TNTs, group=None):
+        """``calculate_nmfp`` for THIS rank's draws when the draws are sharded over the ranks of ``group`` (one process
+        per GPU): the stage that depends on the frequency but not on the draw (``nmfp.py:103-113``) is computed for a
+        slice of the frequency grid per rank and exchanged with one all-gather, instead of being repeated on every
+        rank; the per-draw factorisation and contraction then run locally for all frequencies. ``fgw``: 1-D float64
+        CUDA tensor (the same on every rank); returns this rank's ``(D_local, F)`` tensor, bit-identical to
+        ``calculate_nmfp`` (tiles are computed independently of how they are grouped)."""
+        import torch
+        import torch.distributed as dist
+
+        from . import parallel
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            out = self.calculate_nmfp(fgw, samples, Nvecs, Ts, TNTs)
+            return out if out.dim() == 2 else out[None]
+        if not _is_cuda_tensor(fgw) or fgw.dtype != torch.float64 or fgw.dim() != 1 or fgw.device.index != self.device:
+            raise TypeError("calculate_nmfp_2d needs a 1-D float64 CUDA tensor of frequencies on the pack's device")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        curn, A, G, cA, cG, D, _ = self._draw_arrays(samples)
+        dev = torch.device("cuda", self.device)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        f = fgw.contiguous()
+        F = int(f.shape[0])
+        nt, per = parallel.tile_blocks(F, world)
+        out = torch.empty((D, F), dtype=torch.float64, device=dev)
+
+        def run(pack):
+            zt, at = pack.nmfp_tile_sizes()
+            # this rank's tiles: frequencies [32 * rank * per, 32 * (rank + 1) * per), the tail repeated (padding tiles
+            # are computed like any other and never read)
+            idx = torch.arange(32 * rank * per, 32 * (rank + 1) * per, device=dev).clamp_(max=F - 1)
+            floc = f[idx].contiguous()
+            zloc = torch.empty(per * zt, dtype=torch.float64, device=dev)
+            aloc = torch.empty(per * at, dtype=torch.float64, device=dev)
+            pack.nmfp_stage_a(floc.data_ptr(), 32 * per, zloc.data_ptr(), aloc.data_ptr(), stream=stream)
+            zall = torch.empty(world * per * zt, dtype=torch.float64, device=dev)
+            aall = torch.empty(world * per * at, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(zall, zloc, group=group)
+            dist.all_gather_into_tensor(aall, aloc, group=group)
+            phiinv = torch.empty((D, pack.mvar_total), dtype=torch.float64, device=dev)
+            pack.powerlaw_phiinv([s.Ffreqs for s in self.rn_sigs], A, G, None if curn is None else curn.Ffreqs,
+                                 cA, cG, phiinv.data_ptr(), stream=stream)
+            pack.nmfp_stage_b(f.data_ptr(), F, zall.data_ptr(), aall.data_ptr(), per, phiinv.data_ptr(), D,
+                              out.data_ptr(), stream=stream)
+            return out
+
+        return self._run_verified((Nvecs, Ts, TNTs), run, asynchronous=True)
+
+    def calculate_nmfp(self, fgw, samples, Nvecs, Ts, TNTs):
+        """Fp at ``fgw`` for the noise parameters ``samples`` (reference ``nmfp.py:76-119``)."""
+        import torch
+
+        lists = (Nvecs, Ts, TNTs)
+        curn, A, G, cA, cG, D, batched = self._draw_arrays(samples)
 
         dev = torch.device("cuda", self.device)
         stream = torch.cuda.current_stream(dev).cuda_stream

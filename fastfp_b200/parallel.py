@@ -4,7 +4,9 @@ Every (frequency, draw) output is independent, so the packed pulsar arrays are r
 every rank, the frequency axis is cut into ``world_size`` contiguous shards, each rank sweeps its
 shard for all pulsars, and the per-bin values are assembled with a single
 ``all_gather_into_tensor`` (NCCL over NVLink on GPUs; gloo in the CPU tests). There is no other
-communication on the path. One process per GPU (``torchrun``); ranks read
+communication on the plain-Fp path. The noise-marginalised path shards the DRAW axis (``sharded_draws``) and, in its
+two-dimensional form (``NMFP.calculate_nmfp_2d``), also the frequency axis of its draw-independent stage, whose tiles
+are exchanged with one more all-gather (``tile_blocks``). One process per GPU (``torchrun``); ranks read
 ``RANK``/``LOCAL_RANK``/``WORLD_SIZE`` from the environment.
 """
 from __future__ import annotations
@@ -21,6 +23,18 @@ def shard_bounds(F: int, rank: int, world: int) -> Tuple[int, int, int]:
     lo = min(F, rank * per)
     hi = min(F, lo + per)
     return lo, hi, per
+
+
+def tile_blocks(F: int, world: int) -> Tuple[int, int]:
+    """Two-dimensional sharding of the noise-marginalised sweep: the draw-independent stage works in tiles of 32
+    frequencies; returns ``(nt, per)`` = the number of tiles of ``F`` frequencies and the (even) number of tiles every
+    rank computes, rank ``r`` owning tiles ``[r * per, (r + 1) * per)`` (those beyond ``nt`` are padding)."""
+    if F < 1 or world < 1:
+        raise ValueError("need F >= 1 and world >= 1")
+    nt = -(-F // 32)
+    per = -(-nt // world)
+    per += per & 1
+    return nt, per
 
 
 def sharded_sweep(local_fn: Callable, freqs, group=None, lead_shape=()):

@@ -122,6 +122,23 @@ int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* 
 int fastfp_nmfp_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F,
                       const double* phiinv_var, int64_t D, double* out, int flags, void* stream);
 
+/* The two halves of fastfp_nmfp_sweep as separate calls, for callers that shard the work in two dimensions over
+ * several GPUs (fastfp_b200/parallel.py::sharded_nmfp): stage A -- everything that depends on the frequency but not on
+ * the draw (nmfp.py:103-113: the sin/cos templates through T^T N^-1 and the draw-independent block of Sigma) -- is
+ * computed for a SLICE of the frequency grid per GPU and all-gathered; factor + stage B (nmfp.py:58-74, 114-119) then
+ * run per GPU for its draws on all frequencies. All pointers are device memory on the pack's device.
+ *   fastfp_nmfp_tile_sizes  doubles per 32-frequency tile (all pulsars) of the two stage-A outputs
+ *   fastfp_nmfp_stage_a     z (ceil(F/32) * z_per_tile) and a (ceil(F/32) * a_per_tile) for F frequencies
+ *   fastfp_nmfp_stage_b     z / a hold consecutive blocks of tiles_per_block tiles each (one block per gathered
+ *                           slice; even unless there is one block), together the ceil(F/32) tiles of freqs;
+ *                           out: (D, F) row-major */
+int fastfp_nmfp_tile_sizes(const fastfp_pack_t* pack, int64_t* z_per_tile, int64_t* a_per_tile);
+int fastfp_nmfp_stage_a(const fastfp_pack_t* pack, const double* freqs_dev, int64_t F, double* z_dev, double* a_dev,
+                        void* stream);
+int fastfp_nmfp_stage_b(const fastfp_pack_t* pack, const double* freqs_dev, int64_t F, const double* z_dev,
+                        const double* a_dev, int64_t tiles_per_block, const double* phiinv_var_dev, int64_t D,
+                        double* out_dev, void* stream);
+
 /* fastfp_powerlaw_phiinv: RN_container.get_phiinv for the varying block (nmfp.py:226-234,
  * 247/275 CURN add, 305-315 reciprocal), for D draws and P pulsars at once, on the device.
  *   Ffreqs[p]      (m_var[p]) repeat(k/Tspan,2) of pulsar p (host)

@@ -48,6 +48,9 @@ def _worker(rank, world, port, out_dir):
     mine = {k: v[lo:hi] for k, v in samples.items()}
     g2 = parallel.sharded_draws(lambda a, b: nm(fn, mine, *nmats), D)
     s2 = nm(fn, samples, *nmats)
+    # two-dimensional form: the draw-independent stage computed in frequency slices and all-gathered
+    g3 = parallel.sharded_draws(lambda a, b: nm.calculate_nmfp_2d(fn, mine, *nmats), D)
+    np.save(os.path.join(out_dir, f"nm2d_gathered_{rank}.npy"), g3.cpu().numpy())
     np.save(os.path.join(out_dir, f"nm_gathered_{rank}.npy"), g2.cpu().numpy())
     np.save(os.path.join(out_dir, f"nm_single_{rank}.npy"), s2.cpu().numpy())
     dist.barrier()
@@ -71,3 +74,4 @@ def test_two_gpu_gather_equals_single_gpu_sweep(tmp_path):
         np.testing.assert_array_equal(np.load(tmp_path / f"fp_single_{r}.npy"), ref)  # the two GPUs agree
         np.testing.assert_array_equal(np.load(tmp_path / f"nm_gathered_{r}.npy"), refn)
         np.testing.assert_array_equal(np.load(tmp_path / f"nm_single_{r}.npy"), refn)
+        np.testing.assert_array_equal(np.load(tmp_path / f"nm2d_gathered_{r}.npy"), refn)  # 2-D sharding: same bits

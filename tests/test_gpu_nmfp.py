@@ -235,3 +235,44 @@ def test_nmfp_wide_timing_model_block():
         tt, cond = truth.fp_sweep_truth(freqs, pta.toas, pta.residuals, pta.Nvecs, pta.Ts, sig)
         tv = tt.sum(0).astype(float)
         assert np.all(np.abs(got[d] - tv) <= _tol(tv, cond.sum(0))), d
+
+
+def test_stage_a_blocks_plus_stage_b_equal_the_combined_sweep():
+    """The two halves of the sweep through the C ABI, stage A made in two frequency slices laid out as two blocks
+    (what two ranks would all-gather: fastfp_b200/parallel.py::tile_blocks), stage B on the blocks: bit for bit the
+    combined call. One GPU stands in for the two ranks."""
+    import torch
+
+    from fastfp_b200 import parallel
+
+    pta = synth.make_pta(4, [700, 1203, 333, 901], n_tm=[8, 12, 5, 10], ncomps=30, seed=21)
+    curn = CURN_container(pta.Ffreqs)
+    sigs = [RN_container(q, Ffreqs=pta.Ffreqs, add_curn=True, curn_container=curn) for q in pta.psrs]
+    nm = NMFP(pta.psrs, sigs)
+    mats = (pta.Nvecs, pta.Ts, pta.TNTs)
+    F, D, world = 173, 11, 2  # 6 tiles: blocks of 4 (2 real + padding in the second)
+    f = torch.from_numpy(synth.nmfp_freqs(F, pta.Tspan) * 1.001).cuda()
+    samples = synth.draw_samples(pta, D)
+    want = nm(f, samples, *mats)
+    pack = nm.prepare(*mats)
+    nt, per = parallel.tile_blocks(F, world)
+    assert (nt, per) == (6, 4)
+    zt, at = pack.nmfp_tile_sizes()
+    zall = torch.full((world * per * zt,), float("nan"), dtype=torch.float64, device="cuda")
+    aall = torch.full((world * per * at,), float("nan"), dtype=torch.float64, device="cuda")
+    for r in range(world):
+        idx = torch.arange(32 * r * per, 32 * (r + 1) * per, device="cuda").clamp_(max=F - 1)
+        floc = f[idx].contiguous()
+        pack.nmfp_stage_a(floc.data_ptr(), 32 * per, zall[r * per * zt:].data_ptr(), aall[r * per * at:].data_ptr())
+    curn_, A, G, cA, cG, D_, _ = nm._draw_arrays(samples)
+    phiinv = torch.empty((D, pack.mvar_total), dtype=torch.float64, device="cuda")
+    pack.powerlaw_phiinv([s.Ffreqs for s in sigs], A, G, curn.Ffreqs, cA, cG, phiinv.data_ptr())
+    out = torch.empty((D, F), dtype=torch.float64, device="cuda")
+    pack.nmfp_stage_b(f.data_ptr(), F, zall.data_ptr(), aall.data_ptr(), per, phiinv.data_ptr(), D, out.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int64), want.view(torch.int64))
+    # a single rank: calculate_nmfp_2d is the plain call
+    assert torch.equal(nm.calculate_nmfp_2d(f, samples, *mats).view(torch.int64), want.view(torch.int64))
+    # an odd number of tiles per block is refused when there are several blocks
+    with pytest.raises(fastfp_b200._cabi.FastFpError):
+        pack.nmfp_stage_b(f.data_ptr(), F, zall.data_ptr(), aall.data_ptr(), 3, phiinv.data_ptr(), D, out.data_ptr())

@@ -51,3 +51,14 @@ def test_single_process_is_passthrough():
     f = torch.arange(5, dtype=torch.float64)
     assert torch.equal(parallel.sharded_sweep(lambda x: x + 1, f), f + 1)
     assert parallel.sharded_draws(lambda lo, hi: torch.zeros(hi - lo, 4), 7).shape == (7, 4)
+
+
+def test_tile_blocks_cover_the_grid_with_even_blocks():
+    # two-dimensional nmfp sharding: tiles of 32 frequencies, an even number per rank, all tiles covered once
+    for F, world in [(1, 1), (1, 8), (31, 2), (32, 2), (33, 2), (1000, 2), (10_000, 8), (10_000, 3), (64, 1)]:
+        nt, per = parallel.tile_blocks(F, world)
+        assert nt == -(-F // 32) and per % 2 == 0 and per * world >= nt and (per - 2) * world < nt
+        owners = [t // per for t in range(nt)]
+        assert max(owners) < world
+    with pytest.raises(ValueError):
+        parallel.tile_blocks(0, 2)
