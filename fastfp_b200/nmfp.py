@@ -333,6 +333,8 @@ class NMFP(_PackCache):
             aall = torch.empty(world * per * at, dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(zall, zloc, group=group)
             dist.all_gather_into_tensor(aall, aloc, group=group)
+            if D == 0:  # more ranks than draws: this rank only contributes its stage-A tiles
+                return out
             phiinv = torch.empty((D, pack.mvar_total), dtype=torch.float64, device=dev)
             pack.powerlaw_phiinv([s.Ffreqs for s in self.rn_sigs], A, G, None if curn is None else curn.Ffreqs,
                                  cA, cG, phiinv.data_ptr(), stream=stream)

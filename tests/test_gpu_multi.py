@@ -51,6 +51,13 @@ def _worker(rank, world, port, out_dir):
     # two-dimensional form: the draw-independent stage computed in frequency slices and all-gathered
     g3 = parallel.sharded_draws(lambda a, b: nm.calculate_nmfp_2d(fn, mine, *nmats), D)
     np.save(os.path.join(out_dir, f"nm2d_gathered_{rank}.npy"), g3.cpu().numpy())
+    # fewer draws than ranks and a grid of two tiles: rank 1 has no draw and only padding tiles besides its own
+    one = {k: v[:1] for k, v in samples.items()}
+    lo1, hi1, _ = parallel.shard_bounds(1, rank, world)
+    mine1 = {k: v[lo1:hi1] for k, v in one.items()}
+    g4 = parallel.sharded_draws(lambda a, b: nm.calculate_nmfp_2d(fn[:40], mine1, *nmats), 1)
+    np.save(os.path.join(out_dir, f"nm2d_small_{rank}.npy"), g4.cpu().numpy())
+    np.save(os.path.join(out_dir, f"nm_small_single_{rank}.npy"), nm(fn[:40], one, *nmats).cpu().numpy())
     np.save(os.path.join(out_dir, f"nm_gathered_{rank}.npy"), g2.cpu().numpy())
     np.save(os.path.join(out_dir, f"nm_single_{rank}.npy"), s2.cpu().numpy())
     dist.barrier()
@@ -75,3 +82,6 @@ def test_two_gpu_gather_equals_single_gpu_sweep(tmp_path):
         np.testing.assert_array_equal(np.load(tmp_path / f"nm_gathered_{r}.npy"), refn)
         np.testing.assert_array_equal(np.load(tmp_path / f"nm_single_{r}.npy"), refn)
         np.testing.assert_array_equal(np.load(tmp_path / f"nm2d_gathered_{r}.npy"), refn)  # 2-D sharding: same bits
+        small = np.load(tmp_path / f"nm_small_single_{r}.npy")
+        assert small.shape == (1, 40)
+        np.testing.assert_array_equal(np.load(tmp_path / f"nm2d_small_{r}.npy"), small)
