@@ -15,6 +15,7 @@
 //   stage B (once per (pulsar, draw, frequency)): u = L^-1 z' for 32 frequencies at a time on the
 //           fp64 MMA path, the five m_var-long reductions, the 2x2 solve and the pulsar sum.
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 
@@ -648,8 +649,24 @@ int nmfp_stage_b_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, c
     set_error("stage B: tiles per block must be even when the tiles come in several blocks");
     return FASTFP_ERR_INVALID;
   }
-  // draw batches bound the L^-1 store (~1.5 GiB)
-  const int64_t DB = std::max<int64_t>(NB_DT, std::min<int64_t>(D, ((3LL << 26) / ((int64_t)P * lfw)) / NB_DT * NB_DT));
+  // Draw batches bound the L^-1 store (written by the factor kernel, read by every frequency tile of stage B). One batch
+  // of up to 1.5 GiB is the fastest (C3: 17.7 ms, 2.4 GB of DRAM traffic per sweep, far from binding at ~130 GB/s);
+  // FASTFP_B200_NMFP_LF_MB=64 keeps the store L2-resident instead (batches of whole CTA waves: 0.79 GB per sweep, the
+  // rest being the z' tiles re-read per batch, at 18.1 ms) -- bytes, not time, so it is not the default.
+  static const long lf_mb = getenv("FASTFP_B200_NMFP_LF_MB") ? atol(getenv("FASTFP_B200_NMFP_LF_MB")) : 0;
+  const int64_t per_draw = (int64_t)P * lfw * 8;
+  int64_t DB;
+  if (lf_mb <= 0) {
+    DB = std::max<int64_t>(NB_DT, std::min<int64_t>(D, ((3LL << 26) / ((int64_t)P * lfw)) / NB_DT * NB_DT));
+  } else {
+    int64_t groups = std::max<int64_t>(1, (lf_mb << 20) / (per_draw * NB_DT));          // draw groups that fit the budget
+    const int64_t pairs = (nt32 + 1) / 2;                                                 // CTAs per draw group (NMBV <= 8)
+    if (pairs < pk->num_sms) {                                                            // round down to whole waves
+      const int64_t per_wave = std::max<int64_t>(1, pk->num_sms / pairs);
+      if (groups >= per_wave) groups = groups / per_wave * per_wave;
+    }
+    DB = std::min<int64_t>(std::max<int64_t>(NB_DT, groups * NB_DT), std::max<int64_t>(NB_DT, (D + NB_DT - 1) / NB_DT * NB_DT));
+  }
   if (int rc = ensure(&pk->d_lf, &pk->lf_cap, DB * P * lfw)) return rc;
   double* dLf = pk->d_lf;
   for (int64_t dd = 0; dd < D; dd += DB) {
