@@ -2,8 +2,9 @@
 // digit planes (tcgen05.mma kind::i8, exact int32 accumulation in tensor memory), everything else in fp64.
 //
 // Replaces the body of FastFp.calculate_Fp under jax.vmap (reference fastfp/fastfp.py:69-92, examples/run_fp.py:63)
-// like fp_sweep_kernel.cuh does, for packs whose pulsars fit the tile (basis width m <= 127, n <= 16384 TOAs, diagonal
-// N); the fp64 DMMA kernel stays as the path for everything else. Why: fp64 has no tcgen05 kind, and the DMMA
+// like fp_sweep_kernel.cuh does, for packs with n <= 16384 TOAs per pulsar, a diagonal N and up to 639 basis columns
+// (128 operand rows -- 127 columns + the C^-1 r row -- per pass over the TOAs; wider bases take one pass per row group
+// of 128, the b-sums adding up in the epilogue); the fp64 DMMA kernel stays as the path for everything else. Why: fp64 has no tcgen05 kind, and the DMMA
 // formulation is pinned at 0.68 of the fp64 pipe it has to share with the sincos generation.
 // The INT8 tensor path is a different unit altogether, and integer accumulation is exact.
 //
@@ -11,8 +12,8 @@
 // tests/test_split_precision_emulation.py):
 //   G row j (and the extra row w = C^-1 r):  g = G / 2^e_j with |g| < 1/4,  Qg = rint(g 2^55),
 //        Qg = sum_i d_i 256^(6-i), balanced digits d_i in [-128, 127]  (pack time, i8_planes_kernel)
-//   s, c in [-1, 1]:  Q = rint(x 2^54) = sum_j v_j 256^(6-j), balanced digits (producers: two magic-constant
-//        roundings give the high 26 and the low 28 bits as integers, the bytes of Q + 0x80..80 are the digits + 128)
+//   s, c in [-1, 1]:  Q = rint(x 2^54) = sum_j v_j 256^(6-j), balanced digits (producers: an exponent add and one
+//        F2I.S64.F64; the bytes of Q + 0x80..80 are the digits + 128)
 //   Y_j = 2^(e_j - 13) sum_{g=0..6} 256^-g  sum_{i+j=g} sum_k d_i(k) v_j(k):   28 plane products, one int32
 //        accumulator per weight g (|d v| <= 2^14, 7 products per TOA: exact for n <= 18 724 TOAs)
 //
@@ -49,6 +50,7 @@ constexpr int S_PLANE = NBR * KT;      // 2048 bytes
 constexpr int S_STAGE = NPL * S_PLANE; // 14336 bytes
 constexpr int V_STAGE = KT * 16;       // (t, 1/N) per TOA
 constexpr int SST = 6, VST = 8;        // ring depths (even: a slot is always served by the same producer group)
+constexpr int RS = 640;                // row-scale stride per pulsar: up to 5 row groups of 128 operand rows (m <= 639)
 constexpr int NISSUE = 3;               // MMA-issuing threads (control warps 1-3), each owning a set of accumulators
 // Warp layout: warps 0-3 control (TMA, MMA issue), 4-7 epilogue, 8.. producers. A stage is always produced by 8
 // warps (thread = one frequency x four TOAs); with NPW = 16 two groups of 8 alternate stages, with NPW = 8 one group
@@ -65,8 +67,8 @@ struct Roles {
 static_assert(SST % 2 == 0 && VST % 2 == 0, "ring depths must be even");
 
 struct Args {
-  const unsigned char* planes;   // per pulsar, per stage: [V_STAGE bytes (t, 1/N)][NPL][rows][32] swizzled
-  const double* rowscale;        // [P][128]  2^(e_j - 13), 0 for rows that do not exist
+  const unsigned char* planes;   // per pulsar, per stage: [V_STAGE bytes (t, 1/N)] then per row group [NPL][rows_g][32] swizzled
+  const double* rowscale;        // [P][RS]  2^(e_j - 13), 0 for rows that do not exist
   const PulsarMeta* meta;
   const int* pidx;
   const double* freqs;
@@ -102,9 +104,9 @@ __global__ void i8_rowscale_kernel(const double* __restrict__ packets, const Pul
                                    double* __restrict__ rowscale, int* __restrict__ rowexp, int* __restrict__ bad) {
   const PulsarMeta pm = meta[blockIdx.y];
   const int r = blockIdx.x;
-  if (r >= 128) return;
-  double* rs = rowscale + (size_t)blockIdx.y * 128 + r;
-  int* re = rowexp + (size_t)blockIdx.y * 128 + r;
+  if (r >= RS) return;
+  double* rs = rowscale + (size_t)blockIdx.y * RS + r;
+  int* re = rowexp + (size_t)blockIdx.y * RS + r;
   if (r > pm.m) {
     if (threadIdx.x == 0) { *rs = 0.0; *re = 0; }
     return;
@@ -162,8 +164,10 @@ __global__ void i8_planes_kernel(const double* __restrict__ packets, const Pulsa
     }
     v[kk] = tv;
   }
+  // row groups of 128 operand rows (one accumulator set each, one pass over the TOAs per group): group-major, then
+  // plane-major, so that a (stage, group) is one contiguous TMA copy
   unsigned char* g = out + V_STAGE;
-  const int* re = rowexp + (size_t)blockIdx.y * 128;
+  const int* re = rowexp + (size_t)blockIdx.y * RS;
   for (int e = threadIdx.x; e < rows * KT; e += blockDim.x) {
     const int r = e / KT, kk = e - r * KT;
     const int i = st * KT + kk;
@@ -176,9 +180,11 @@ __global__ void i8_planes_kernel(const double* __restrict__ packets, const Pulsa
     // Qg = rint(val 2^(55 - e)): exact scaling, |Qg| <= 2^53; balanced base-256 digits = bytes of Qg + 0x80..80, - 128
     const long long Q = __double2ll_rn(scalbn(val, 55 - re[r]));
     const unsigned long long U = (unsigned long long)(Q + 0x0080808080808080LL) ^ 0x0080808080808080ULL;
-    const int off = swz32(r, kk);
+    const int grp = r >> 7, rl = r & 127, rows_g = min(128, rows - 128 * grp);
+    unsigned char* gg = g + (size_t)grp * (NPL * 128 * KT);
+    const int off = swz32(rl, kk);
 #pragma unroll
-    for (int p = 0; p < NPL; ++p) g[(size_t)p * rows * KT + off] = (unsigned char)(U >> (8 * (6 - p)));
+    for (int p = 0; p < NPL; ++p) gg[(size_t)p * rows_g * KT + off] = (unsigned char)(U >> (8 * (6 - p)));
   }
 }
 
@@ -354,19 +360,25 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       unsigned char* gdst = sm.G;
       for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x) {
         const PulsarMeta pm = ar.meta[ar.pidx[item / ar.ntile]];
-        const uint32_t gbytes = (uint32_t)(NPL * pm.i8_rows * KT);
-        const unsigned char* src = ar.planes + pm.i8_off;
-        for (int c = 0; c < pm.i8_nst; ++c, ++k) {
-          if (k >= VST) wait_wd<2000>(&sm.v_empty[sv], vpar ^ 1u, 1, k);
-          mbar_expect_tx(&sm.v_full[sv], V_STAGE);
-          tma_load_1d(sm.V + sv * V_STAGE, src, V_STAGE, &sm.v_full[sv]);
-          if (k >= (uint32_t)ar.gst) wait_wd<2000>(&sm.g_empty[sg], gpar ^ 1u, 2, k);
-          if (k >= (uint32_t)ar.gst) FFP_TRACE(0, k - (uint32_t)ar.gst);   // MMAs of stage k - gst have completed (seen by the TMA thread)
-          mbar_expect_tx(&sm.g_full[sg], gbytes);
-          tma_load_1d(gdst, src + V_STAGE, gbytes, &sm.g_full[sg]);
-          src += V_STAGE + gbytes;
-          if (++sv == VST) { sv = 0; vpar ^= 1u; }
-          if (++sg == (uint32_t)ar.gst) { sg = 0; gpar ^= 1u; gdst = sm.G; } else gdst += ar.gslot;
+        const size_t stage_bytes = (size_t)V_STAGE + (size_t)NPL * pm.i8_rows * KT;
+        const int ng = (pm.i8_rows + 127) >> 7;
+        for (int grp = 0; grp < ng; ++grp) {  // one pass over the TOAs per group of 128 operand rows
+          const int rows_g = min(128, pm.i8_rows - 128 * grp);
+          const uint32_t gbytes = (uint32_t)(NPL * rows_g * KT);
+          const unsigned char* src = ar.planes + pm.i8_off;
+          const size_t goff = (size_t)V_STAGE + (size_t)grp * (NPL * 128 * KT);
+          for (int c = 0; c < pm.i8_nst; ++c, ++k) {
+            if (k >= VST) wait_wd<2000>(&sm.v_empty[sv], vpar ^ 1u, 1, k);
+            mbar_expect_tx(&sm.v_full[sv], V_STAGE);
+            tma_load_1d(sm.V + sv * V_STAGE, src, V_STAGE, &sm.v_full[sv]);
+            if (k >= (uint32_t)ar.gst) wait_wd<2000>(&sm.g_empty[sg], gpar ^ 1u, 2, k);
+            if (k >= (uint32_t)ar.gst) FFP_TRACE(0, k - (uint32_t)ar.gst);   // MMAs of stage k - gst have completed (seen by the TMA thread)
+            mbar_expect_tx(&sm.g_full[sg], gbytes);
+            tma_load_1d(gdst, src + goff, gbytes, &sm.g_full[sg]);
+            src += stage_bytes;
+            if (++sv == VST) { sv = 0; vpar ^= 1u; }
+            if (++sg == (uint32_t)ar.gst) { sg = 0; gpar ^= 1u; gdst = sm.G; } else gdst += ar.gslot;
+          }
         }
       }
     } else if (wid >= 1) {
@@ -382,50 +394,57 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NBR >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t tmu = __shfl_sync(0xffffffffu, tm, 0);
       const uint32_t g0 = smem_u32(sm.G), s0 = smem_u32(sm.S);
-      uint32_t k = 0, it = 0;
+      uint32_t k = 0, ps = 0;  // global stage counter; pass counter (one pass = one row group of one item)
       uint32_t sg = 0, gpar = 0, ss = 0, spar = 0, ga = g0, sa = s0;  // ring positions, parities, slot addresses
-      for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x) {
         const int pi = ar.pidx[item / ar.ntile];
-        const uint32_t aplane16 = __shfl_sync(0xffffffffu, (uint32_t)(ar.meta[pi].i8_rows * KT) >> 4, 0);
+        const int rows = __shfl_sync(0xffffffffu, ar.meta[pi].i8_rows, 0);
         const int nst = __shfl_sync(0xffffffffu, ar.meta[pi].i8_nst, 0);
-        if (it > 0) wait_wd<0>(sm.acc_empty, (it - 1) & 1u, 3, it);  // the epilogue has drained the accumulators
-        for (int c = 0; c < nst; ++c, ++k) {
-          wait_wd<0>(&sm.g_full[sg], gpar, 4, k);
-          wait_wd<0>(&sm.s_full[ss], spar, 5, k);
-          tc_fence_after();
-          if (wid == 1 && leader) FFP_TRACE(1, k);   // issuer 0 sees stage k complete
-          const uint32_t da_lo = ((ga >> 4) & 0x3fffu) | (1u << 16);
-          const uint32_t db_lo = ((sa >> 4) & 0x3fffu) | (1u << 16);
-          if (leader) {
-            if (wid == 1) issue_stage<0>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
-            else if (wid == 2) issue_stage<1>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
-            else issue_stage<2>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
-            umma_commit(&sm.g_empty[sg]);  // each issuer's commit arrives when ITS MMAs above have read their operands
-            umma_commit(&sm.s_empty[ss]);
-            if (wid == 1) FFP_TRACE(2, k);           // issuer 0 has issued its MMAs of stage k
+        for (int grp = 0; 128 * grp < rows; ++grp, ++ps) {
+          const uint32_t aplane16 = (uint32_t)(min(128, rows - 128 * grp) * KT) >> 4;
+          if (ps > 0) wait_wd<0>(sm.acc_empty, (ps - 1) & 1u, 3, ps);  // the epilogue has drained the accumulators
+          for (int c = 0; c < nst; ++c, ++k) {
+            wait_wd<0>(&sm.g_full[sg], gpar, 4, k);
+            wait_wd<0>(&sm.s_full[ss], spar, 5, k);
+            tc_fence_after();
+            if (wid == 1 && leader) FFP_TRACE(1, k);   // issuer 0 sees stage k complete
+            const uint32_t da_lo = ((ga >> 4) & 0x3fffu) | (1u << 16);
+            const uint32_t db_lo = ((sa >> 4) & 0x3fffu) | (1u << 16);
+            if (leader) {
+              if (wid == 1) issue_stage<0>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
+              else if (wid == 2) issue_stage<1>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
+              else issue_stage<2>(tmu, da_lo, db_lo, aplane16, idesc, c == 0);
+              umma_commit(&sm.g_empty[sg]);  // each issuer's commit arrives when ITS MMAs above have read their operands
+              umma_commit(&sm.s_empty[ss]);
+              if (wid == 1) FFP_TRACE(2, k);           // issuer 0 has issued its MMAs of stage k
+            }
+            __syncwarp();
+            if (++sg == (uint32_t)ar.gst) { sg = 0; gpar ^= 1u; ga = g0; } else ga += (uint32_t)ar.gslot;
+            if (++ss == SST) { ss = 0; spar ^= 1u; sa = s0; } else sa += S_STAGE;
           }
+          if (leader) umma_commit(sm.acc_full);
           __syncwarp();
-          if (++sg == (uint32_t)ar.gst) { sg = 0; gpar ^= 1u; ga = g0; } else ga += (uint32_t)ar.gslot;
-          if (++ss == SST) { ss = 0; spar ^= 1u; sa = s0; } else sa += S_STAGE;
         }
-        if (leader) umma_commit(sm.acc_full);
-        __syncwarp();
       }
     }
   } else if (wid < 8) {
     // ================= epilogue warpgroup: one TMEM lane quarter per warp =================
     reg_set_inc<R::REGS_EPI>();
     const int ew = wid - 4;
-    const int row = 32 * ew + lane;
-    uint32_t it = 0;
+    const int lrow = 32 * ew + lane;   // TMEM lane = operand row inside the row group
+    uint32_t it = 0, ps = 0;  // items; passes (one per row group of an item)
     for (int item = blockIdx.x; item < ar.nwork; item += gridDim.x, ++it) {
       const int gp = item / ar.ntile, ft = item - gp * ar.ntile;
       const int p = ar.pidx[gp];
       const PulsarMeta pm = ar.meta[p];
       const int64_t f0 = (int64_t)ft * NF;
-      const double rs = ar.rowscale[(size_t)p * 128 + row];
-      const bool has_rows = 32 * ew < pm.i8_rows;  // warp-uniform
-      wait_wd<100000>(sm.acc_full, it & 1u, 6, it);
+      // bases wider than 127 columns take one pass per group of 128 operand rows; the b-sums of the groups add up in
+      // `part`, the w row sits in the last group
+      for (int grp = 0; 128 * grp < pm.i8_rows; ++grp, ++ps) {
+      const int row = 128 * grp + lrow;
+      const double rs = ar.rowscale[(size_t)p * RS + row];
+      const bool has_rows = 128 * grp + 32 * ew < pm.i8_rows;  // warp-uniform
+      wait_wd<100000>(sm.acc_full, ps & 1u, 6, ps);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < NF; c0 += 8) {
@@ -509,12 +528,14 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
         if ((lane & 3) == 0) {
           const int q = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
           double* o = sm.part + ((size_t)ew * NF + c0 + q) * 3;
-          o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+          if (grp == 0) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+          else { o[0] += v[0]; o[1] += v[1]; o[2] += v[2]; }   // (this warp's own slots: no other writer)
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sm.acc_empty);  // tensor memory may be overwritten by the next item
+      if (lane == 0) mbar_arrive(sm.acc_empty);  // tensor memory may be overwritten by the next pass
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // partial sums and the w-row values of the 4 warps are visible
       const uint32_t buf = it & 1u;
       if (ew == 0) {
@@ -630,6 +651,9 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
       const bool fast = __all_sync(0xffffffffu, fabs(omega) * pm.tabs_max <= 0.999 * FFP_SINCOS_MAX);
       double s3[2] = {0.0, 0.0};  // s N^-1 s, s N^-1 c
       const int nst = pm.i8_nst;
+      // one pass over the TOAs per group of 128 operand rows (bases wider than 127 columns): the planes are produced
+      // again for every pass, the quadratic sums only in the first
+      for (int rg = 0; 128 * rg < pm.i8_rows; ++rg, kbase += (uint32_t)nst) {
       const int c0 = NG == 1 ? 0 : (int)((kbase ^ grp) & 1u);
       for (int c = c0; c < nst; c += NG) {
         const uint32_t k = kbase + (uint32_t)c;
@@ -656,11 +680,13 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
             sv4[e] = s1; cv4[e] = c1;
           }
         }
+        if (rg == 0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double sn = sv4[e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
-          s3[0] = fma(sn, sv4[e], s3[0]);
-          s3[1] = fma(sn, cv4[e], s3[1]);
+          for (int e = 0; e < 4; ++e) {
+            const double sn = sv4[e] * ninv[e];   // c N^-1 c follows from sum 1/N - s N^-1 s (epilogue)
+            s3[0] = fma(sn, sv4[e], s3[0]);
+            s3[1] = fma(sn, cv4[e], s3[1]);
+          }
         }
         // ---- the group's previous stage is complete in shared memory: announce it now (see above)
         __syncwarp();
@@ -676,7 +702,7 @@ __global__ void __launch_bounds__(Roles<NPW>::THREADS, 1) fp_sweep_i8_kernel(con
         if (pw == 0 && lane == 0) FFP_TRACE(5, k);   // planes of stage k stored
         pend = (int)ss;
       }
-      kbase += (uint32_t)nst;
+      }
       // the two sums of frequency f: over the 8 lanes that share it (lane bits 2..4), then published per group
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -786,7 +812,7 @@ int run_i8_peak(int kind, int iters, double* tops, double* ms_out) {
 bool i8_eligible(const fastfp_pack* pk) {
   if (pk->ecorr) return false;
   for (const PulsarMeta& pm : pk->meta)
-    if (pm.m + 1 > 128 || pm.n > 16384) return false;
+    if (pm.m + 1 > i8::RS || pm.n > 16384) return false;
   return true;
 }
 
@@ -798,7 +824,8 @@ int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
   int64_t off = 0;
   int rows_max = 0, nst_max = 0;
   for (PulsarMeta& pm : pk->meta) {
-    // rows padded to 32: every plane then starts on a 1024-byte boundary of the (1024-aligned) ring, the alignment
+    // rows (basis + the w row; more than 128 of them form row groups, one pass over the TOAs each) padded to 32:
+    // every plane then starts on a 1024-byte boundary of the (1024-aligned) ring, the alignment
     // the operand descriptors of all swizzle modes accept; rows beyond the padding are never loaded (the MMA reads
     // 128 rows per plane, the tail comes from the next plane and lands in output lanes nobody reads)
     pm.i8_rows = (pm.m + 1 + 31) / 32 * 32;
@@ -812,12 +839,13 @@ int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
   // the last plane of the last stage is read 128 rows deep by the MMA only from shared memory; the global buffer
   // needs no slack, but keep the allocation 16-byte granular for the bulk copies
   FFP_CUDA(cudaMalloc(&pk->d_i8, (size_t)off + 16));
-  FFP_CUDA(cudaMalloc(&pk->d_i8_scale, (size_t)P * 128 * sizeof(double)));
+  FFP_CUDA(cudaMalloc(&pk->d_i8_scale, (size_t)P * i8::RS * sizeof(double)));
+  FFP_CUDA(cudaMemsetAsync(pk->d_i8_scale, 0, (size_t)P * i8::RS * sizeof(double), st));
   int *d_exp = nullptr, *d_bad = nullptr;
-  FFP_CUDA(cudaMalloc(&d_exp, (size_t)P * 128 * sizeof(int)));
+  FFP_CUDA(cudaMalloc(&d_exp, (size_t)P * i8::RS * sizeof(int)));
   FFP_CUDA(cudaMalloc(&d_bad, (size_t)P * sizeof(int)));
   FFP_CUDA(cudaMemsetAsync(d_bad, 0, (size_t)P * sizeof(int), st));
-  i8::i8_rowscale_kernel<<<dim3(128, P), 256, 0, st>>>(pk->d_packets, pk->d_meta, pk->d_i8_scale, d_exp, d_bad);
+  i8::i8_rowscale_kernel<<<dim3(rows_max, P), 256, 0, st>>>(pk->d_packets, pk->d_meta, pk->d_i8_scale, d_exp, d_bad);
   i8::i8_planes_kernel<<<dim3(nst_max, P), 256, 0, st>>>(pk->d_packets, pk->d_meta, d_exp, pk->d_i8);
   g_launches += 2;
   cudaError_t e = cudaGetLastError();
@@ -842,7 +870,7 @@ int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
     FFP_CUDA(cudaMalloc(&pk->d_pidx_all, sizeof(int) * P));
     FFP_CUDA(cudaMemcpy(pk->d_pidx_all, idx.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
   }
-  pk->bytes += off + (int64_t)P * 128 * 8;
+  pk->bytes += off + (int64_t)P * i8::RS * 8;
   pk->i8_ok = true;
   return 0;
 }
@@ -866,7 +894,7 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   if (nwork > 0x7fffffffLL) { set_error("frequency batch too large for one launch"); return -1; }
   a.ntile = (int)ntile;
   a.nwork = (int)nwork;
-  a.gslot = NPL * pk->i8_rows_max * KT;
+  a.gslot = NPL * (pk->i8_rows_max < 128 ? pk->i8_rows_max : 128) * KT;  // one row group
   const size_t budget = 220 * 1024 - SMEM_FIXED;
   int gst = (int)(budget / a.gslot);
   gst = gst > 8 ? 8 : gst;

@@ -77,7 +77,7 @@ int fastfp_fp_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F, d
  * compute the same quantities to the same parity bar:
  *   FASTFP_PATH_I8    the tensor-core kernel: Y = G [s c] as an error-free product of 8-bit digit planes
  *                     (tcgen05.mma kind::i8, exact int32 accumulation in tensor memory), ~2.5x faster;
- *                     available when every pulsar has m <= 127 basis columns, n <= 16384 TOAs, a diagonal N
+ *                     available when every pulsar has m <= 639 basis columns, n <= 16384 TOAs, a diagonal N
  *                     and finite data (fastfp_pack_set_path returns FASTFP_ERR_UNSUPPORTED otherwise);
  *   FASTFP_PATH_FP64  the fp64 DMMA kernel (always available; block-N packs and wide bases use it);
  *   FASTFP_PATH_AUTO  (default) the tensor kernel when available.
