@@ -208,12 +208,13 @@ class Pack:
 
     def set_path(self, path: str) -> None:
         """Kernel of the plain-Fp sweep: "auto" (default: the INT8 tensor-core kernel when the pack has digit
-        planes), "fp64" (the DMMA kernel) or "i8" (raises if the pack cannot take it)."""
+        planes), "fp64" (the DMMA kernel) or "i8" (raises unless every pulsar fits); ``path`` then
+        reads "fp64", "i8" or "mixed" (auto, with the pulsars the tensor kernel does not take on the fp64 kernel)."""
         check(load().fastfp_pack_set_path(self._h, self.PATHS[path]))
 
     @property
     def path(self) -> str:
-        return {1: "fp64", 2: "i8"}[load().fastfp_pack_path(self._h)]
+        return {1: "fp64", 2: "i8", 3: "mixed"}[load().fastfp_pack_path(self._h)]
 
     def factor_info(self):
         """Per-pulsar status of the one-time Cholesky (0 = fine, j+1 = pivot j not positive)."""

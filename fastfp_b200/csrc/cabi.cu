@@ -165,7 +165,7 @@ static void set_ninv_sums(fastfp_pack* pk, const double* const* Nvecs) {
 static void pack_free(fastfp_pack* pk) {
   if (!pk) return;
   DeviceGuard g(pk->device);
-  for (auto& gr : pk->groups) cudaFree(gr.d_pidx);
+  for (auto& gr : pk->groups) { cudaFree(gr.d_pidx); cudaFree(gr.d_pidx_rest); }
   cudaFree(pk->d_meta); cudaFree(pk->d_packets); cudaFree(pk->d_L); cudaFree(pk->d_info);
   cudaFree(pk->d_S0); cudaFree(pk->d_zr); cudaFree(pk->d_slab); cudaFree(pk->d_counter); cudaFree(pk->d_done_mask);
   cudaFree(pk->d_terms); cudaFree(pk->d_freqs); cudaFree(pk->d_out); cudaFree(pk->d_scratch); cudaFree(pk->d_lf);
@@ -226,9 +226,9 @@ int fastfp_pack_set_path(fastfp_pack_t* pk, int path) {
     set_error("fastfp_pack_set_path: invalid argument");
     return FASTFP_ERR_INVALID;
   }
-  if (path == FASTFP_PATH_I8 && !pk->i8_ok) {
-    set_error("fastfp_pack_set_path: this pack has no INT8 digit planes (block-diagonal N, m > 127, n > 16384 or "
-              "non-finite data)");
+  if (path == FASTFP_PATH_I8 && !(pk->i8_ok && pk->i8_all())) {
+    set_error("fastfp_pack_set_path: not every pulsar of this pack has INT8 digit planes (block-diagonal N, m > 639, "
+              "n > 16384 or non-finite data); FASTFP_PATH_AUTO sweeps those on the fp64 kernel");
     return FASTFP_ERR_UNSUPPORTED;
   }
   pk->path = path;
@@ -237,7 +237,7 @@ int fastfp_pack_set_path(fastfp_pack_t* pk, int path) {
 
 int fastfp_pack_path(const fastfp_pack_t* pk) {
   if (!pk) return FASTFP_ERR_INVALID;
-  return pk->use_i8() ? FASTFP_PATH_I8 : FASTFP_PATH_FP64;
+  return pk->use_i8() ? (pk->i8_all() ? FASTFP_PATH_I8 : FASTFP_PATH_MIXED) : FASTFP_PATH_FP64;
 }
 
 int fastfp_nmfp_pack_create(int device, int P, const int64_t* n, const int64_t* m,
@@ -377,9 +377,7 @@ static const int64_t kTermBudgetDoubles = 1LL << 27;  // 1 GiB
 // per-pulsar terms of one frequency batch on the path the pack is set to
 static int sweep_terms(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
                        double* d_inner = nullptr) {
-  const bool i8 = pk->use_i8();
-  return i8 ? launch_fp_sweep_i8(pk, d_freqs, F, d_terms, st, d_inner)
-            : launch_fp_sweep(pk, d_freqs, F, d_terms, st, nullptr, d_inner);
+  return launch_sweep(pk, d_freqs, F, d_terms, st, nullptr, d_inner);
 }
 
 static int fp_run(const fastfp_pack* pk, const double* freqs, int64_t F, double* out, int flags,

@@ -113,6 +113,8 @@ struct Group {  // pulsars that share one kernel instantiation
   KernelCfg cfg;
   int count;
   int* d_pidx;  // device array of pulsar indices
+  int count_rest = 0;          // ... those of them the tensor sweep does not take (build_i8_planes), when it takes some
+  int* d_pidx_rest = nullptr;
 };
 
 }  // namespace ffp
@@ -137,7 +139,8 @@ struct fastfp_pack {
   // INT8 tensor-core path (fp_sweep_i8.cu): digit planes of G, per-row scales; chosen per pack
   unsigned char* d_i8 = nullptr;
   double* d_i8_scale = nullptr;   // [P][128]
-  int* d_pidx_all = nullptr;      // identity pulsar list
+  int* d_pidx_all = nullptr;      // pulsars on the tensor sweep (all of them, or those that fit: n <= 16384, finite planes)
+  int i8_count = 0;               // their number; the others stay on the fp64 kernel in the same sweep
   bool i8_ok = false;             // the planes exist (every pulsar fits the tile, all values finite)
   int i8_rows_max = 0;
   int64_t i8_bytes = 0;
@@ -146,6 +149,7 @@ struct fastfp_pack {
   // the faster kernel: profiles/README.md); FASTFP_PATH_FP64 forces the DMMA kernel
   static constexpr bool kAutoPrefersI8 = true;
   bool use_i8() const { return i8_ok && (path == 2 || (path == 0 && kAutoPrefersI8)); }
+  bool i8_all() const { return i8_count == P; }
   int64_t bytes = 0;
   int64_t mvar_total = 0;
   int mvar_max = 0;
@@ -220,7 +224,10 @@ struct NmfpOut {      // stage-A outputs of the nmfp path (null for plain Fp)
   int mvmax;          // padded width of the per-draw block (multiple of 8)
 };
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
-                    cudaStream_t st, const NmfpOut* nm = nullptr, double* d_inner = nullptr);
+                    cudaStream_t st, const NmfpOut* nm = nullptr, double* d_inner = nullptr, bool rest_only = false);
+// the sweep on the path(s) the pack is set to: the tensor kernel for the pulsars it takes, the fp64 kernel for the rest
+int launch_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
+                 const NmfpOut* nm = nullptr, double* d_inner = nullptr);
 int launch_reduce_terms(const double* d_terms, int P, int64_t F, double* d_out, cudaStream_t st);
 // fp_sweep_i8.cu
 bool i8_eligible(const fastfp_pack* pk);

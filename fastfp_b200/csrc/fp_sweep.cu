@@ -36,7 +36,7 @@ __global__ void reduce_terms_kernel(const double* __restrict__ terms, int P, int
 }
 
 int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms,
-                    cudaStream_t st, const NmfpOut* nm, double* d_inner) {
+                    cudaStream_t st, const NmfpOut* nm, double* d_inner, bool rest_only) {
 #ifdef FFP_DEBUG_SWITCHES  // profiling builds only; the shipped library is compiled without it
   static const int dbg = getenv("FASTFP_DBG") ? atoi(getenv("FASTFP_DBG")) : 0;
 #endif
@@ -56,7 +56,13 @@ int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, dou
 #ifdef FFP_DEBUG_SWITCHES
   a.dbg = dbg;
 #endif
-  for (const Group& g : pk->groups) {
+  for (const Group& g0 : pk->groups) {
+    Group g = g0;
+    if (rest_only) {  // only the pulsars the tensor sweep left out
+      if (g0.count_rest == 0) continue;
+      g.count = g0.count_rest;
+      g.d_pidx = g0.d_pidx_rest;
+    }
     int rc;
     if (g.cfg.wmw == 8) rc = dispatch_sweep_xwide(pk, g, a, nm != nullptr, st);
     else if (g.cfg.wmw == 4) rc = dispatch_sweep_wide(pk, g, a, nm != nullptr, st);
@@ -66,6 +72,13 @@ int launch_fp_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, dou
     if (rc) return rc;
   }
   return 0;
+}
+
+int launch_sweep(const fastfp_pack* pk, const double* d_freqs, int64_t F, double* d_terms, cudaStream_t st,
+                 const NmfpOut* nm, double* d_inner) {
+  if (!pk->use_i8()) return launch_fp_sweep(pk, d_freqs, F, d_terms, st, nm, d_inner);
+  if (int rc = launch_fp_sweep_i8(pk, d_freqs, F, d_terms, st, d_inner, nm)) return rc;
+  return pk->i8_all() ? 0 : launch_fp_sweep(pk, d_freqs, F, d_terms, st, nm, d_inner, true);
 }
 
 int launch_reduce_terms(const double* d_terms, int P, int64_t F, double* d_out, cudaStream_t st) {

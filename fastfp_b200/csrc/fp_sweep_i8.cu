@@ -104,7 +104,7 @@ __global__ void i8_rowscale_kernel(const double* __restrict__ packets, const Pul
                                    double* __restrict__ rowscale, int* __restrict__ rowexp, int* __restrict__ bad) {
   const PulsarMeta pm = meta[blockIdx.y];
   const int r = blockIdx.x;
-  if (r >= RS) return;
+  if (r >= RS || pm.i8_nst == 0) return;  // (pulsars the tensor sweep does not take have no stages)
   double* rs = rowscale + (size_t)blockIdx.y * RS + r;
   int* re = rowexp + (size_t)blockIdx.y * RS + r;
   if (r > pm.m) {
@@ -809,28 +809,35 @@ int run_i8_peak(int kind, int iters, double* tops, double* ms_out) {
 // A pack can take the tensor path when every pulsar fits the tile: diagonal N, m + 1 <= 128 rows (the basis rows and
 // the w row), n <= 16384 TOAs (int32 accumulators: 7 products of |digit|^2 <= 2^14 per TOA stay below 2^31
 // up to 18 724 TOAs).
+// which pulsars the tensor sweep can take: diagonal N (pack-wide), up to RS operand rows, n <= 16384 (exactness of the
+// int32 accumulators); the others of a pack stay on the fp64 kernel in the same sweep
+static bool i8_takes(const fastfp_pack* pk, const PulsarMeta& pm) {
+  return !pk->ecorr && pm.m + 1 <= i8::RS && pm.n <= 16384;
+}
 bool i8_eligible(const fastfp_pack* pk) {
-  if (pk->ecorr) return false;
   for (const PulsarMeta& pm : pk->meta)
-    if (pm.m + 1 > i8::RS || pm.n > 16384) return false;
-  return true;
+    if (i8_takes(pk, pm)) return true;
+  return false;
 }
 
 // lay out and build the digit planes from the fp64 packets (after launch_fp_precompute); sets pk->i8_ok
 int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
   pk->i8_ok = false;
+  pk->i8_count = 0;
   if (!i8_eligible(pk)) return 0;
   const int P = pk->P;
   int64_t off = 0;
   int rows_max = 0, nst_max = 0;
   for (PulsarMeta& pm : pk->meta) {
+    pm.i8_rows = pm.i8_nst = 0;
+    pm.i8_off = off;
+    if (!i8_takes(pk, pm)) continue;
     // rows (basis + the w row; more than 128 of them form row groups, one pass over the TOAs each) padded to 32:
     // every plane then starts on a 1024-byte boundary of the (1024-aligned) ring, the alignment
     // the operand descriptors of all swizzle modes accept; rows beyond the padding are never loaded (the MMA reads
     // 128 rows per plane, the tail comes from the next plane and lands in output lanes nobody reads)
     pm.i8_rows = (pm.m + 1 + 31) / 32 * 32;
     pm.i8_nst = (pm.n + i8::KT - 1) / i8::KT;
-    pm.i8_off = off;
     off += (int64_t)pm.i8_nst * (i8::V_STAGE + i8::NPL * pm.i8_rows * i8::KT);
     rows_max = pm.i8_rows > rows_max ? pm.i8_rows : rows_max;
     nst_max = pm.i8_nst > nst_max ? pm.i8_nst : nst_max;
@@ -855,20 +862,37 @@ int build_i8_planes(fastfp_pack* pk, cudaStream_t st) {
   cudaFree(d_exp);
   cudaFree(d_bad);
   if (e != cudaSuccess) return cuda_fail(e, "build_i8_planes");
-  bool ok = true;
-  for (int p = 0; p < P; ++p) ok = ok && bad[p] == 0 && (p >= (int)pk->info.size() || pk->info[p] == 0);
+  // pulsars with a non-finite G or w (singular Sigma, NaN data) cannot be carried by integer planes: fp64 kernel
+  std::vector<int> take, rest_flag(P, 1);
+  for (int p = 0; p < P; ++p) {
+    const bool ok = pk->meta[p].i8_nst > 0 && bad[p] == 0 && (p >= (int)pk->info.size() || pk->info[p] == 0);
+    if (ok) { take.push_back(p); rest_flag[p] = 0; }
+  }
   pk->i8_rows_max = rows_max;
   pk->i8_bytes = off;
-  if (!ok) {  // non-finite G or w (singular Sigma, NaN data): the integer planes cannot carry it
+  if (take.empty()) {
     cudaFree(pk->d_i8); cudaFree(pk->d_i8_scale);
     pk->d_i8 = nullptr; pk->d_i8_scale = nullptr;
     return 0;
   }
-  if (!pk->d_pidx_all) {
-    std::vector<int> idx(P);
-    for (int p = 0; p < P; ++p) idx[p] = p;
-    FFP_CUDA(cudaMalloc(&pk->d_pidx_all, sizeof(int) * P));
-    FFP_CUDA(cudaMemcpy(pk->d_pidx_all, idx.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+  cudaFree(pk->d_pidx_all);
+  pk->d_pidx_all = nullptr;
+  FFP_CUDA(cudaMalloc(&pk->d_pidx_all, sizeof(int) * take.size()));
+  FFP_CUDA(cudaMemcpy(pk->d_pidx_all, take.data(), sizeof(int) * take.size(), cudaMemcpyHostToDevice));
+  pk->i8_count = (int)take.size();
+  // the complement, per kernel family of the fp64 sweep
+  for (Group& g : pk->groups) {
+    std::vector<int> all((size_t)g.count), rest;
+    FFP_CUDA(cudaMemcpy(all.data(), g.d_pidx, sizeof(int) * g.count, cudaMemcpyDeviceToHost));
+    for (int p : all)
+      if (rest_flag[p]) rest.push_back(p);
+    cudaFree(g.d_pidx_rest);
+    g.d_pidx_rest = nullptr;
+    g.count_rest = (int)rest.size();
+    if (g.count_rest) {
+      FFP_CUDA(cudaMalloc(&g.d_pidx_rest, sizeof(int) * rest.size()));
+      FFP_CUDA(cudaMemcpy(g.d_pidx_rest, rest.data(), sizeof(int) * rest.size(), cudaMemcpyHostToDevice));
+    }
   }
   pk->bytes += off + (int64_t)P * i8::RS * 8;
   pk->i8_ok = true;
@@ -890,7 +914,7 @@ int launch_fp_sweep_i8(const fastfp_pack* pk, const double* d_freqs, int64_t F, 
   a.Z = nm ? nm->Z : nullptr;
   a.A = nm ? nm->A : nullptr;
   a.mvpad = nm ? nm->mvmax : 0;
-  const int64_t ntile = (F + NF - 1) / NF, nwork = ntile * pk->P;
+  const int64_t ntile = (F + NF - 1) / NF, nwork = ntile * pk->i8_count;  // the pulsars this kernel takes
   if (nwork > 0x7fffffffLL) { set_error("frequency batch too large for one launch"); return -1; }
   a.ntile = (int)ntile;
   a.nwork = (int)nwork;

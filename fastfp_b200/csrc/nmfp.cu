@@ -633,8 +633,7 @@ int nmfp_stage_a_impl(const fastfp_pack* pk, const double* d_freqs, int64_t F, d
   FFP_CUDA(cudaMemsetAsync(dA, 0, (size_t)P * nt32 * 160 * 8, st));
   NmfpOut nm{dZ, dA, MV};
   // on the tensor path when the pack carries digit planes, else on the fp64 DMMA kernel
-  return pk->use_i8() ? launch_fp_sweep_i8(pk, d_freqs, F, nullptr, st, nullptr, &nm)
-                      : launch_fp_sweep(pk, d_freqs, F, nullptr, st, &nm);
+  return launch_sweep(pk, d_freqs, F, nullptr, st, &nm);
 }
 
 // Factor + stage B for D draws on tiles that already exist: Z and A hold blocks of nt_blk tiles ([block][P][nt_blk]),

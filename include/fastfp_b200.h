@@ -76,15 +76,18 @@ int fastfp_fp_sweep(const fastfp_pack_t* pack, const double* freqs, int64_t F, d
 /* Which kernel runs the frequency sweep of this pack (the plain-Fp sweep, the Fe sweep, stage A of nmfp). Both
  * compute the same quantities to the same parity bar:
  *   FASTFP_PATH_I8    the tensor-core kernel: Y = G [s c] as an error-free product of 8-bit digit planes
- *                     (tcgen05.mma kind::i8, exact int32 accumulation in tensor memory), ~2.5x faster;
- *                     available when every pulsar has m <= 639 basis columns, n <= 16384 TOAs, a diagonal N
- *                     and finite data (fastfp_pack_set_path returns FASTFP_ERR_UNSUPPORTED otherwise);
- *   FASTFP_PATH_FP64  the fp64 DMMA kernel (always available; block-N packs and wide bases use it);
- *   FASTFP_PATH_AUTO  (default) the tensor kernel when available.
- * fastfp_pack_path returns the path in effect (never AUTO). */
+ *                     (tcgen05.mma kind::i8, exact int32 accumulation in tensor memory), 1.4-3.6x faster;
+ *                     takes pulsars with m <= 639 basis columns, n <= 16384 TOAs and finite data in packs with a
+ *                     diagonal N (fastfp_pack_set_path(I8) returns FASTFP_ERR_UNSUPPORTED unless EVERY pulsar fits);
+ *   FASTFP_PATH_FP64  the fp64 DMMA kernel (always available; block-N packs use it);
+ *   FASTFP_PATH_AUTO  (default) the tensor kernel for the pulsars it takes, the fp64 kernel for the others of the
+ *                     same pack in the same sweep.
+ * fastfp_pack_path returns the path in effect (never AUTO): FP64, I8 (all pulsars) or MIXED (AUTO with some
+ * pulsars on either kernel). */
 #define FASTFP_PATH_AUTO 0
 #define FASTFP_PATH_FP64 1
 #define FASTFP_PATH_I8 2
+#define FASTFP_PATH_MIXED 3
 int fastfp_pack_set_path(fastfp_pack_t* pack, int path);
 int fastfp_pack_path(const fastfp_pack_t* pack);
 

@@ -13,10 +13,10 @@ from oracle import truth
 pytestmark = pytest.mark.gpu
 
 
-def _against_truth(pta, freqs, path):
+def _against_truth(pta, freqs, path, expect=None):
     mats = (pta.Nvecs, pta.Ts, pta.sigmas)
     fp = fastfp_b200.FastFp(pta.psrs, path=path)
-    assert fp.prepare(*mats).path == path
+    assert fp.prepare(*mats).path == (expect or path)
     got = fp.per_pulsar_terms(freqs, *mats)
     args = (freqs, pta.toas, pta.residuals, *mats)
     ora = o.fp_sweep(*args, per_pulsar=True)
@@ -39,13 +39,29 @@ def test_widest_basis_and_longest_pulsar_the_tensor_path_takes():
     assert np.all(np.abs(t8 - t64) <= 2 * tol)  # the same statistic from both kernels
 
 
-def test_one_toa_too_many_hands_over_to_the_fp64_kernel():
-    pta = synth.make_pta(2, [16385, 300], n_tm=[7, 7], ncomps=60, seed=32)
+def test_one_toa_too_many_goes_to_the_fp64_kernel_pulsar_by_pulsar():
+    # pulsar 0 is one TOA beyond the exactness bound of the int32 accumulators: the fp64 kernel sweeps it, the tensor
+    # kernel the other two, in the same call
+    pta = synth.make_pta(3, [16385, 300, 1207], n_tm=[7, 7, 9], ncomps=60, seed=32)
     mats = (pta.Nvecs, pta.Ts, pta.sigmas)
-    assert fastfp_b200.FastFp(pta.psrs).prepare(*mats).path == "fp64"        # auto
-    assert fastfp_b200.FastFp(pta.psrs, path="prefer-i8").prepare(*mats).path == "fp64"
+    assert fastfp_b200.FastFp(pta.psrs).prepare(*mats).path == "mixed"        # auto
+    assert fastfp_b200.FastFp(pta.psrs, path="prefer-i8").prepare(*mats).path == "mixed"
     with pytest.raises(_cabi.FastFpError):
         fastfp_b200.FastFp(pta.psrs, path="i8").prepare(*mats)
+    freqs = np.concatenate((synth.fp_freqs(30), np.array([1.0, 17.5, 60.0]) / pta.Tspan))
+    tm, tol = _against_truth(pta, freqs, "auto", expect="mixed")
+    t64, _ = _against_truth(pta, freqs, "fp64")
+    np.testing.assert_array_equal(tm[0], t64[0])            # pulsar 0 ran on the fp64 kernel: the same bits
+    assert np.all(np.abs(tm - t64) <= 2 * tol)
+    # the noise-marginalised stage A mixes the same way: the (D, F) result against the all-fp64 run
+    from fastfp_b200 import NMFP, RN_container
+
+    sigs = [RN_container(q, Ffreqs=pta.Ffreqs) for q in pta.psrs]
+    samples = {k: v for k, v in synth.draw_samples(pta, 3).items() if not k.startswith("gw_")}
+    fn = synth.nmfp_freqs(40, pta.Tspan) * 1.003
+    a = NMFP(pta.psrs, sigs)(fn, samples, pta.Nvecs, pta.Ts, pta.TNTs)
+    b = NMFP(pta.psrs, sigs, path="fp64")(fn, samples, pta.Nvecs, pta.Ts, pta.TNTs)
+    np.testing.assert_allclose(a, b, rtol=1e-6)
 
 
 @pytest.mark.parametrize("n_tm,ncomps", [(8, 60), (68, 60), (136, 60), (140, 60), (519, 60)])
