@@ -54,10 +54,18 @@ WORKLOADS = {
     "C2": dict(kind="fp", P=45, n=5000, F_per_gpu=10_000, scaling="weak"),
     "C3": dict(kind="nmfp", P=45, n=5000, F=1_000, D_per_gpu=1_000, scaling="weak"),
     "C5": dict(kind="nmfp", P=68, n=10_000, F=10_000, D_total=10_000, blockn=True, epoch=4, scaling="strong"),
+    # wide bases (real pulsars reach several hundred columns): 12 timing-model + 2 x 149 Fourier columns
+    "W": dict(kind="fp", P=16, n=5000, F_per_gpu=4096, ncomps=149, scaling="weak"),
     "T": dict(kind="fp", P=3, n=300, F_per_gpu=256, scaling="weak"),  # tiny: tests/test_bench_contract.py
     "TN": dict(kind="nmfp", P=3, n=300, F=64, D_per_gpu=16, scaling="weak"),
 }
 M_BASIS = 72
+
+
+def m_of(wl):
+    """basis width of a workload: 12 timing-model columns + 2 per Fourier component (30 unless the workload says otherwise)"""
+    return 12 + 2 * wl.get("ncomps", 30)
+
 M_VAR = 60  # per-draw (red-noise) block of the basis: 30 Fourier components
 METRIC = "Fp evals/sec (freqs x pulsars x draws)"
 
@@ -124,9 +132,9 @@ def config_of(key, wl, gpus):
                 "n_gpus": gpus, "scaling": wl["scaling"]}
     F = total_F(wl, gpus)
     per = "in total, sharded over the GPUs" if "F_total" in wl else f"= {wl['F_per_gpu']} per GPU"
-    name = (f"{key}: Fp sweep, {wl['P']} pulsars x {wl['n']} TOAs, m={M_BASIS} (12 timing-model + 60 Fourier), "
+    name = (f"{key}: Fp sweep, {wl['P']} pulsars x {wl['n']} TOAs, m={m_of(wl)} (12 timing-model + {m_of(wl) - 12} Fourier), "
             f"{F} frequencies {per}, {gpus} GPU(s), red+white Woodbury C, fp64")
-    return {"workload": name, "P": wl["P"], "n_toas": wl["n"], "m": M_BASIS, "F": F, "D": 1, "n_gpus": gpus,
+    return {"workload": name, "P": wl["P"], "n_toas": wl["n"], "m": m_of(wl), "F": F, "D": 1, "n_gpus": gpus,
             "scaling": wl["scaling"]}
 
 
@@ -187,7 +195,7 @@ def cpu_reference_rate(wl, world=1, steps=1, warmup=0, target_s=12.0):
     from oracle import fp_oracle
 
     cores = os.cpu_count() or 1
-    pta = synth.make_pta(wl["P"], wl["n"])
+    pta = synth.make_pta(wl["P"], wl["n"], ncomps=wl.get("ncomps", 30))
     F_all = total_F(wl, world)
     grid = synth.fp_freqs(F_all)
     common = (pta.toas, pta.residuals, pta.Nvecs, pta.Ts, pta.sigmas)
@@ -221,7 +229,7 @@ def nmfp_problem(wl):
     """Inputs of an nmfp workload: (pta, containers, Nvecs-or-BlockNvecs, TNTs)."""
     from fastfp_b200 import BlockNvec, CURN_container, RN_container, synth
 
-    pta = synth.make_pta(wl["P"], wl["n"])
+    pta = synth.make_pta(wl["P"], wl["n"], ncomps=wl.get("ncomps", 30))
     curn = CURN_container(pta.Ffreqs)
     sigs = [RN_container(q, Ffreqs=pta.Ffreqs, add_curn=True, curn_container=curn) for q in pta.psrs]
     if not wl.get("blockn"):
@@ -249,7 +257,7 @@ def cpu_reference_rate_nmfp(wl, world=1, steps=1, warmup=0, target_s=12.0):
     from oracle import fp_oracle
 
     cores = os.cpu_count() or 1
-    pta = synth.make_pta(wl["P"], wl["n"])
+    pta = synth.make_pta(wl["P"], wl["n"], ncomps=wl.get("ncomps", 30))
     F_all = wl["F"]
     Fs = min(F_all, 1024)
     freqs = synth.nmfp_freqs(F_all, pta.Tspan)[:: max(1, F_all // Fs)][:Fs]
@@ -387,7 +395,8 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
     from fastfp_b200 import _cabi, parallel, synth
 
     torch, rank, world, dev = ctx.torch, ctx.rank, ctx.world, ctx.dev
-    pta = synth.make_pta(wl["P"], wl["n"])
+    pta = synth.make_pta(wl["P"], wl["n"], ncomps=wl.get("ncomps", 30))
+    m_basis = m_of(wl)
     F_total = total_F(wl, world)
     freqs_np = synth.fp_freqs(F_total)
     freqs_host = torch.from_numpy(freqs_np).pin_memory()
@@ -488,6 +497,10 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
     ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     shard = freqs_dev[lo:hi].contiguous()
     nk = 3 if ms_step < 1000.0 else 1
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.6 and ms_step < 1000.0:  # the checks above ran on the host: clocks back up
+        fp.calculate_Fp(shard, *mats)
+        torch.cuda.synchronize()
     fp.calculate_Fp(shard[:1024], *mats)
     torch.cuda.synchronize()
     ks.record()
@@ -505,23 +518,24 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
     evals_step = float(F_total) * wl["P"]
     evals_kernel = float(hi - lo) * wl["P"]
     hbm_peak, peak_src = measured_peaks()
-    ach_gbs = evals_kernel * bytes_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e9
+    ach_gbs = evals_kernel * bytes_per_eval(wl["n"], m_basis) / (kern_ms * 1e-3) / 1e9
     traffic, traffic_src = measured_traffic(key)
     fp64_peak, _ = _cabi.fp64_peak(1, 20000, device=ctx.local)  # DMMA loop, same pipe as DFMA
-    ach_tf = evals_kernel * flops_per_eval(wl["n"], M_BASIS) / (kern_ms * 1e-3) / 1e12
+    ach_tf = evals_kernel * flops_per_eval(wl["n"], m_basis) / (kern_ms * 1e-3) / 1e12
     if sweep_path == "i8":
         # The contraction runs on the INT8 tensor path: Y = G [s c] as 28 products of 8-bit digit planes
         # (tcgen05.mma kind::i8, exact int32 accumulation). Algorithmic integer ops per eval: 28 plane products
         # x 2 (multiply, add) x 2 columns (sin, cos) x (m + 1) rows (basis + the C^-1 r row) x n TOAs.
         i8_peak, _ = _cabi.fp64_peak(17, 2000, device=ctx.local)
         i8_shape, _ = _cabi.fp64_peak(18, 4000, device=ctx.local)
-        ops_eval = 28.0 * 2.0 * 2.0 * (M_BASIS + 1) * wl["n"]
+        ops_eval = 28.0 * 2.0 * 2.0 * (m_basis + 1) * wl["n"]
         ach_top = evals_kernel * ops_eval / (kern_ms * 1e-3) / 1e12
         nst = -(-wl["n"] // 32)
-        items = wl["P"] * -(-(hi - lo) // 32)
+        rows_pad = 32 * -(-(m_basis + 1) // 32)
+        passes = -(-rows_pad // 128)  # row groups of 128 operand rows: one pass over the TOAs each
+        items = wl["P"] * -(-(hi - lo) // 32) * passes
         exec_top = items * nst * 28.0 * 2.0 * 128 * 64 * 32 / (kern_ms * 1e-3) / 1e12
-        rows_pad = 32 * -(-(M_BASIS + 1) // 32)
-        smem_stage = 28.0 * 6144 + 7.0 * rows_pad * 32 + 14336
+        smem_stage = 28.0 * 6144 + 7.0 * min(rows_pad, 128) * 32 + 14336
         sm_count = torch.cuda.get_device_properties(ctx.local).multi_processor_count
         smem_peak = 128.0 * sm_count * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0) * 1e6 / 1e9
         roofline = {
@@ -533,7 +547,7 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
             "kernel": "fp_sweep_i8_kernel (persistent, warp-specialised: TMA / MMA issue / epilogue / sincos producers)",
             "kernel_ms": kern_ms, "ops_per_eval": ops_eval,
             "shape_bound": {"achieved": exec_top, "peak": i8_shape, "unit": "TOP/s", "frac": exec_top / i8_shape,
-                            "note": "executed MMA work (128-row operand, of which m + 1 = 73 rows are real) against the "
+                            "note": "executed MMA work (128-row operands, m + 1 real rows in all) against the "
                                     "same 28-product stage issued back to back (kind 18): an M=128 N=64 K=32 MMA reads 6 KB "
                                     "of operands from shared memory = 48 cycles at 128 B/clk, against 32 cycles of tensor "
                                     "time -- shared-memory operand bandwidth is what binds this formulation (TMEM holds "
@@ -558,7 +572,7 @@ def run_fp(key, wl, ctx, steps, warmup, with_cpu_baseline):
                     "peak_source": "measured live on this GPU: fastfp_fp64_peak (mma.sync.m8n8k4.f64 loop); "
                                    "MEASURED_PEAKS.json holds no fp64 figure",
                     "kernel": "fp_sweep_kernel (persistent, warp-specialised)", "kernel_ms": kern_ms,
-                    "flops_per_eval": flops_per_eval(wl["n"], M_BASIS),
+                    "flops_per_eval": flops_per_eval(wl["n"], m_basis),
                     "note": "algorithmic flops (4m+10)n per eval: Y = G[s c] and the five weighted sums; the "
                             "sincos generation that must also run on this pipe is not counted"}
     line = {
@@ -806,7 +820,7 @@ def main():
     line = runner(key, wl, ctx, args.steps, args.warmup, not args.no_cpu_baseline)
     if args.workload is None and not args.no_secondary:
         sec = {}
-        for k2 in ("C2", "C3"):
+        for k2 in ("C2", "C3", "W"):
             w2 = WORKLOADS[k2]
             r2 = run_nmfp if w2["kind"] == "nmfp" else run_fp
             res = r2(k2, w2, ctx, min(args.steps, 10), 3, False)
