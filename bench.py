@@ -833,6 +833,11 @@ def main():
         for k2, l2 in line.get("secondary", {}).items():
             bad += [f"{k2}.{name}" for name, c in l2.get("checks", {}).items() if c.get("ok") is False]
         line["checks_failed"] = bad
+        # tuning switches of the library that change the schedule, never the results: recorded when set
+        knobs = {k: os.environ[k] for k in ("FASTFP_B200_PATH", "FASTFP_B200_I8_NPW", "FASTFP_B200_NMFP_LF_MB")
+                 if k in os.environ}
+        if knobs:
+            line["env"] = knobs
         emit(line)
         if bad:
             print(f"bench.py: result checks FAILED: {bad}", file=sys.stderr)
